@@ -1,0 +1,108 @@
+/*
+ * mclip_b200.h -- C ABI of libmclip_b200.so: the B200 (sm_100a) contrastive-loss hot path.
+ *
+ * The reference (psmyth94/mamba-clip) has no FFI: its boundary is the Python class
+ * `ClipLoss` (src/mamba_clip/loss.py:56-147).  `mamba_clip_b200.loss.ClipLoss` keeps that class
+ * API and binds the entry points below with ctypes.  All pointers are raw
+ * DEVICE pointers owned by the caller (PyTorch allocates everything); the library never allocates
+ * or frees device memory, never synchronises the host, and launches only on the stream handed in.
+ * Every entry point returns 0 on success or an MCLIP_ERR_* code; `mclip_last_error()` returns a
+ * thread-local message for the last failure.  Nothing aborts.
+ *
+ * Arithmetic: inputs are f32, bf16 or f16 row-major matrices; all statistics, the loss and
+ * d(logit_scale) are f32; products are accumulated in f32 (tcgen05 tensor cores for bf16/f16
+ * inputs, FFMA for f32 inputs).  The B x B logits matrix is never written to memory.
+ */
+#ifndef MCLIP_B200_H_
+#define MCLIP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCLIP_ABI_VERSION 1
+
+enum { MCLIP_DTYPE_F32 = 0, MCLIP_DTYPE_BF16 = 1, MCLIP_DTYPE_F16 = 2 };
+enum { MCLIP_PATH_AUTO = 0, MCLIP_PATH_SIMT = 1, MCLIP_PATH_TCGEN05 = 2 };
+enum { MCLIP_OP_ROW_LSE = 0, MCLIP_OP_BLOCK_GRAD = 1 };
+enum {
+  MCLIP_OK = 0,
+  MCLIP_ERR_INVALID = 1,      /* bad shape / pointer / alignment / enum */
+  MCLIP_ERR_CUDA = 2,         /* a CUDA runtime/driver call failed (message has the CUDA error) */
+  MCLIP_ERR_UNSUPPORTED = 3,  /* device is not sm_100, or the forced path cannot run this shape */
+  MCLIP_ERR_WORKSPACE = 4     /* workspace smaller than mclip_workspace_bytes() */
+};
+
+/* ABI version of the loaded library (== MCLIP_ABI_VERSION of the header it was built from). */
+int mclip_abi_version(void);
+
+/* Thread-local, NUL-terminated description of the last error on this thread ("" if none). */
+const char* mclip_last_error(void);
+
+/* 0 if `device` can run the kernels (compute capability 10.x); writes major*10+minor to *sm. */
+int mclip_device_supported(int device, int* sm);
+
+/* Which path MCLIP_PATH_AUTO would take for this problem (MCLIP_PATH_SIMT / MCLIP_PATH_TCGEN05). */
+int mclip_select_path(int64_t M, int64_t N, int64_t D, int64_t ldx, int64_t ldy, int dtype, int op);
+
+/* Bytes of scratch `ws` the given op needs for this problem (256-byte aligned pointer expected). */
+int mclip_workspace_bytes(int64_t M, int64_t N, int64_t D, int dtype, int op, int path, size_t* bytes);
+
+/*
+ * Row log-sum-exp of one logits block, without materialising it.
+ *   S = logit_scale * X @ Y^T            X: [M, D] (ldx), Y: [N, D] (ldy), row-major
+ *   lse[i]  = log sum_j exp(S[i, j])                          (natural log, f32)
+ *   diag[i] = <X[i], Y[i + diag_off]>  (raw dot product, 0 when i + diag_off is outside [0, N))
+ * Replaces, for one side of the loss, reference loss.py:102-111 (`logit_scale * a @ b.T`) fused with
+ * the log_softmax half of F.cross_entropy at loss.py:143-144; `diag_off` is the label offset of
+ * loss.py:80-81 (`labels + num_logits * rank`).  Called twice per forward: (image rows, all text) and
+ * (text rows, all image).  `logit_scale` is a device scalar (no host sync).  `diag` may be NULL.
+ */
+int mclip_row_lse(const void* X, const void* Y, int64_t M, int64_t N, int64_t D, int64_t ldx, int64_t ldy,
+                  int dtype, const float* logit_scale, int64_t diag_off, float* lse, float* diag,
+                  void* ws, size_t ws_bytes, int path, void* cuda_stream);
+
+/*
+ * Gradient of one logits block w.r.t. its row operand, recomputing the block (never stored):
+ *   s_ij  = logit_scale * <X[i], Y[j]>
+ *   G_ij  = w_row * exp(s_ij - lse_x[i]) + w_col * exp(s_ij - lse_y[j]) - w_diag * [j == i + diag_off]
+ *   dX    = (grad_out * logit_scale * inv_2n) * G @ Y          written in the input dtype, [M, D] (lddx)
+ *   rowdot[i] = sum_j exp(s_ij - lse_x[i]) * <X[i], Y[j]>      (f32; feeds d logit_scale)
+ * Replaces the implicit autograd graph of loss.py:102-111,142-145 (MmBackward + LogSoftmaxBackward +
+ * NllLossBackward) for one side.  `lse_y` may be NULL iff w_col == 0 (local_loss without
+ * gather_with_grad: own-row terms only).  `grad_out` is a device scalar (GradScaler's scale reaches
+ * the loss through it, reference train.py:59-63) or NULL for 1.  `rowdot` may be NULL.
+ */
+int mclip_block_grad(const void* X, const void* Y, int64_t M, int64_t N, int64_t D, int64_t ldx, int64_t ldy,
+                     int dtype, const float* logit_scale, const float* grad_out, const float* lse_x,
+                     const float* lse_y, int64_t diag_off, float w_row, float w_col, float w_diag,
+                     float inv_2n, void* dX, int64_t lddx, float* rowdot, void* ws, size_t ws_bytes,
+                     int path, void* cuda_stream);
+
+/*
+ * loss = (1 / (2 n)) * sum_i (row_lse[i] + col_lse[i] - 2 * logit_scale * diag[i])
+ * i.e. (CE(logits_per_image) + CE(logits_per_text)) / 2 of loss.py:142-145 for the n local samples.
+ */
+int mclip_loss_finalize(const float* row_lse, const float* col_lse, const float* diag, int64_t n,
+                        const float* logit_scale, float* loss, void* cuda_stream);
+
+/*
+ * t   = sum_i (u[i] + v[i] - 2 * diag[i])            (the rank's partial of sum_ij G_ij C_ij * 2n)
+ * dls = grad_out * scale * t                         (scale = 1/(2 n_ls); grad_out NULL -> 1)
+ * Replaces the d(logit_scale) branch of autograd through `logit_scale * features` (loss.py:102-111).
+ * Writes t_out[0] = t and dls_out[0] = dls.
+ */
+int mclip_dls_finalize(const float* u, const float* v, const float* diag, int64_t n, const float* grad_out,
+                       float scale, float* t_out, float* dls_out, void* cuda_stream);
+
+/* Number of kernel launches issued by this library on the calling thread since load (bench.py's
+ * "gpu_launches" counter). */
+int64_t mclip_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCLIP_B200_H_ */

@@ -1,0 +1,93 @@
+// Shared declarations for libmclip_b200 (internal; the public ABI is include/mclip_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include "../../include/mclip_b200.h"
+
+namespace mclip {
+
+// ---- error plumbing (thread-local message, never abort) ------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+void count_launch(int n = 1);
+
+#define MCLIP_CUDA_OK(expr)                                              \
+  do {                                                                   \
+    cudaError_t _e = (expr);                                             \
+    if (_e != cudaSuccess) return ::mclip::cuda_fail(_e, #expr);         \
+  } while (0)
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Problem descriptors passed from the ABI layer to the path-specific launchers.
+struct RowLseArgs {
+  const void* X; const void* Y;
+  int64_t M, N, D, ldx, ldy;
+  int dtype;
+  const float* logit_scale;
+  int64_t diag_off;
+  float* lse;
+  float* diag;       // may be null
+  void* ws; size_t ws_bytes;
+  cudaStream_t stream;
+};
+
+struct BlockGradArgs {
+  const void* X; const void* Y;
+  int64_t M, N, D, ldx, ldy;
+  int dtype;
+  const float* logit_scale;
+  const float* grad_out;  // may be null (== 1)
+  const float* lse_x;
+  const float* lse_y;     // may be null iff w_col == 0
+  int64_t diag_off;
+  float w_row, w_col, w_diag, inv_2n;
+  void* dX; int64_t lddx;
+  float* rowdot;          // may be null
+  void* ws; size_t ws_bytes;
+  cudaStream_t stream;
+};
+
+// SIMT (FFMA, fp32-exact) path -- simt_kernels.cu
+size_t simt_row_lse_ws(int64_t M, int64_t N, int64_t D);
+int simt_row_lse(const RowLseArgs& a);
+size_t simt_block_grad_ws(int64_t M, int64_t N, int64_t D);
+int simt_block_grad(const BlockGradArgs& a);
+
+// tcgen05 / TMEM / TMA path -- tc_kernels.cu
+bool tc_supported(int64_t M, int64_t N, int64_t D, int64_t ldx, int64_t ldy, int dtype, int op);
+size_t tc_row_lse_ws(int64_t M, int64_t N, int64_t D);
+int tc_row_lse(const RowLseArgs& a);
+size_t tc_block_grad_ws(int64_t M, int64_t N, int64_t D);
+int tc_block_grad(const BlockGradArgs& a);
+
+// shared small kernels -- simt_kernels.cu
+// merge `nsplit` partial (max2, sum) pairs per row into a natural-log LSE.
+int launch_lse_merge(const float* part_m2, const float* part_s, int nsplit, int64_t M, float* lse,
+                     cudaStream_t stream);
+int launch_loss_finalize(const float* row_lse, const float* col_lse, const float* diag, int64_t n,
+                         const float* logit_scale, float* loss, cudaStream_t stream);
+int launch_dls_finalize(const float* u, const float* v, const float* diag, int64_t n, const float* grad_out,
+                        float scale, float* t_out, float* dls_out, cudaStream_t stream);
+
+// ---- dtype helpers -------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+
+}  // namespace mclip

@@ -1,0 +1,116 @@
+"""The oracle restatements against the golden vectors produced by the real reference
+(tests/golden/make_golden.py).  CPU only."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import clip_oracle as O
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+SINGLE = np.load(os.path.join(GOLD, "single.npz"))
+RANKS = np.load(os.path.join(GOLD, "ranks.npz"))
+SINGLE_CASES = json.loads(str(SINGLE["cases"]))
+RANK_CASES = json.loads(str(RANKS["cases"]))
+
+
+def projector(dim):
+    g = torch.Generator().manual_seed(4242)
+    return torch.randn(dim, 8, generator=g, dtype=torch.float64)
+
+
+def check_grad(gold, key, g, tol, case):
+    """Relative L2 error, with an absolute floor for saturated-softmax cases whose fp32 reference
+    gradient is pure rounding noise (|dX| ~ 1e-12): floor = 1e-6 x the gradient's natural scale
+    go*ls/(2B)*sqrt(B)."""
+    g = g.double()
+    floor = 1e-6 * case["go"] * case["ls"] / (2 * case["B"]) * case["B"] ** 0.5
+    gn = float(gold[key + "_norm"])
+    assert abs(float(g.norm()) - gn) <= tol * gn + floor
+    if key + "_full" in gold:
+        ref = torch.from_numpy(gold[key + "_full"]).double()
+        assert float((g - ref).norm()) <= tol * float(ref.norm()) + floor
+    else:
+        ref = torch.from_numpy(gold[key + "_proj"])
+        assert float((g @ projector(g.shape[1]) - ref).norm()) <= tol * float(ref.norm()) + 8 * floor
+
+
+def inputs_for(case):
+    img, txt = O.make_features(case["B"], case["D"], seed=case["seed"], correlated=case["corr"])
+    if case["bf16"]:
+        img, txt = img.bfloat16().float(), txt.bfloat16().float()
+    return img, txt
+
+
+@pytest.mark.parametrize("k", range(len(SINGLE_CASES)))
+def test_port_single_matches_reference(k):
+    case = SINGLE_CASES[k]
+    img, txt = inputs_for(case)
+    r = O.ref_port_single(img, txt, case["ls"], grad_output=case["go"])
+    # same ops on the same machine: should agree to rounding
+    assert abs(float(r.loss) - float(SINGLE[f"c{k}_loss"])) <= 2e-6 * max(1.0, abs(float(SINGLE[f"c{k}_loss"])))
+    assert abs(float(r.d_logit_scale) - float(SINGLE[f"c{k}_dls"])) <= 2e-5 * abs(float(SINGLE[f"c{k}_dls"])) + 1e-9
+    check_grad(SINGLE, f"c{k}_di", r.d_image, 1e-5, case)
+    check_grad(SINGLE, f"c{k}_dt", r.d_text, 1e-5, case)
+
+
+@pytest.mark.parametrize("k", range(len(SINGLE_CASES)))
+def test_closed_form_single_matches_reference(k):
+    case = SINGLE_CASES[k]
+    img, txt = inputs_for(case)
+    r = O.closed_form(img, txt, case["ls"], 1, 0, False, False, grad_output=case["go"], chunk=48)
+    # fp64 closed form vs the fp32 reference: reference-vs-fp64 <= ~2e-7; the peaky ls=100
+    # correlated cases have losses ~1e-6 where fp32 itself only resolves ~1e-7 absolute
+    assert abs(float(r.loss) - float(SINGLE[f"c{k}_loss"])) <= 3e-6 * max(1.0, abs(float(SINGLE[f"c{k}_loss"]))) + 2e-7
+    dls = float(SINGLE[f"c{k}_dls"])
+    assert abs(float(r.d_logit_scale) - dls) <= 3e-5 * abs(dls) + 2e-7 * case["go"]
+    check_grad(SINGLE, f"c{k}_di", r.d_image, 2e-5, case)
+    check_grad(SINGLE, f"c{k}_dt", r.d_text, 2e-5, case)
+
+
+@pytest.mark.parametrize("k", range(len(RANK_CASES)))
+def test_rank_emulation_matches_gloo_reference(k):
+    case = RANK_CASES[k]
+    W, Bl = case["W"], case["Bl"]
+    img, txt = O.make_features(W * Bl, case["D"], seed=case["seed"], correlated=case["corr"])
+    port = O.ref_port_ranks(img, txt, case["ls"], W, case["local_loss"], case["gwg"], grad_output=case["go"])
+    for r in range(W):
+        gl = float(RANKS[f"c{k}_r{r}_loss"])
+        gd = float(RANKS[f"c{k}_r{r}_dls"])
+        gi = torch.from_numpy(RANKS[f"c{k}_r{r}_di"])
+        gt = torch.from_numpy(RANKS[f"c{k}_r{r}_dt"])
+        assert abs(float(port[r].loss) - gl) <= 2e-6 * max(1.0, abs(gl))
+        assert abs(float(port[r].d_logit_scale) - gd) <= 2e-5 * abs(gd) + 1e-8
+        assert O.rel_err(port[r].d_image, gi) <= 1e-5
+        assert O.rel_err(port[r].d_text, gt) <= 1e-5
+        cf = O.closed_form(img, txt, case["ls"], W, r, case["local_loss"], case["gwg"],
+                           grad_output=case["go"], chunk=5)
+        assert abs(float(cf.loss) - gl) <= 3e-6 * max(1.0, abs(gl))
+        # fp32 reference loses ~eps*go absolute to cancellation when the softmax is saturated
+        assert abs(float(cf.d_logit_scale) - gd) <= 3e-5 * abs(gd) + 2e-7 * case["go"]
+        # fp64 vs the fp32 reference: absolute floor for the saturated (correlated, ls=30) cases
+        floor = 1e-6 * case["go"] * case["ls"] / (2 * Bl) * Bl ** 0.5
+        assert float((cf.d_image - gi.double()).norm()) <= 2e-5 * float(gi.norm()) + floor
+        assert float((cf.d_text - gt.double()).norm()) <= 2e-5 * float(gt.norm()) + floor
+
+
+def test_block_primitives_compose_to_closed_form():
+    """block_row_lse / block_grad (the CPU statement of the two device primitives) reproduce the
+    closed form when composed the way the host layer composes the kernels."""
+    W, Bl, D, ls, go = 2, 12, 32, 20.0, 3.0
+    img, txt = O.make_features(W * Bl, D, seed=7, correlated=True)
+    for r in range(W):
+        lo, hi = r * Bl, (r + 1) * Bl
+        row_lse_all, _ = O.block_row_lse(img, txt, ls)
+        col_lse_all, _ = O.block_row_lse(txt, img, ls)
+        a = go * ls / (2 * Bl)
+        dI, u = O.block_grad(img[lo:hi], txt, ls, row_lse_all[lo:hi], col_lse_all, lo, 1, 1, 2, a)
+        dT, v = O.block_grad(txt[lo:hi], img, ls, col_lse_all[lo:hi], row_lse_all, lo, 1, 1, 2, a)
+        cf = O.closed_form(img, txt, ls, W, r, True, True, grad_output=go)
+        assert O.rel_err(dI, cf.d_image) < 1e-12
+        assert O.rel_err(dT, cf.d_text) < 1e-12
+        diag = (img[lo:hi].double() * txt[lo:hi].double()).sum(1)
+        dls = go / (2 * Bl) * float((u + v - 2 * diag).sum())
+        assert abs(dls - float(cf.d_logit_scale)) < 1e-12 * max(1.0, abs(dls))
