@@ -1,0 +1,188 @@
+"""ctypes binding of libmclip_b200.so (include/mclip_b200.h) + the tensor-level backend the loss uses.
+
+There is no CPU implementation here on purpose: if the library is missing, or a tensor is not on a
+CUDA device, the calls raise.  (tests/ may install an oracle-backed stand-in through
+`set_backend_override` to exercise the host logic under gloo on CPU.)
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional, Tuple
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmclip_b200.so")
+
+ABI_VERSION = 1
+DTYPE_CODES = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
+PATH_AUTO, PATH_SIMT, PATH_TCGEN05 = 0, 1, 2
+OP_ROW_LSE, OP_BLOCK_GRAD = 0, 1
+
+_c_f32p = ctypes.c_void_p
+_SIGNATURES = {
+    "mclip_abi_version": (ctypes.c_int, []),
+    "mclip_last_error": (ctypes.c_char_p, []),
+    "mclip_launch_count": (ctypes.c_int64, []),
+    "mclip_device_supported": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_int)]),
+    "mclip_select_path": (ctypes.c_int, [ctypes.c_int64] * 5 + [ctypes.c_int, ctypes.c_int]),
+    "mclip_workspace_bytes": (ctypes.c_int, [ctypes.c_int64] * 3 + [ctypes.c_int] * 3 + [ctypes.POINTER(ctypes.c_size_t)]),
+    "mclip_row_lse": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int64] * 5 + [ctypes.c_int, _c_f32p,
+                                     ctypes.c_int64, _c_f32p, _c_f32p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
+                                     ctypes.c_void_p]),
+    "mclip_block_grad": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int64] * 5 + [ctypes.c_int, _c_f32p,
+                                        _c_f32p, _c_f32p, _c_f32p, ctypes.c_int64] + [ctypes.c_float] * 4 +
+                         [ctypes.c_void_p, ctypes.c_int64, _c_f32p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
+                          ctypes.c_void_p]),
+    "mclip_loss_finalize": (ctypes.c_int, [_c_f32p, _c_f32p, _c_f32p, ctypes.c_int64, _c_f32p, _c_f32p, ctypes.c_void_p]),
+    "mclip_dls_finalize": (ctypes.c_int, [_c_f32p, _c_f32p, _c_f32p, ctypes.c_int64, _c_f32p, ctypes.c_float, _c_f32p,
+                                          _c_f32p, ctypes.c_void_p]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def load_library(path: Optional[str] = None) -> ctypes.CDLL:
+    """dlopen the C-ABI library and bind every symbol the header declares.  Raises if it is missing."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise RuntimeError(
+            f"{p} not found: build it with `python -m mamba_clip_b200.build` (nvcc, sm_100a). "
+            "mamba_clip_b200 has no CPU or PyTorch fallback.")
+    lib = ctypes.CDLL(p)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    got = lib.mclip_abi_version()
+    if got != ABI_VERSION:
+        raise RuntimeError(f"libmclip_b200 ABI {got} != expected {ABI_VERSION}; rebuild the library")
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _check(lib, rc: int, what: str):
+    if rc != 0:
+        msg = lib.mclip_last_error().decode("utf-8", "replace")
+        exc = ValueError if rc == 1 else RuntimeError
+        raise exc(f"{what} failed (code {rc}): {msg}")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+class CudaBackend:
+    """Tensor-level wrapper: allocates outputs/workspace with torch, passes raw pointers + the current
+    CUDA stream to the C ABI.  No host synchronisation anywhere."""
+
+    name = "cuda"
+
+    def __init__(self, path: int = PATH_AUTO):
+        self.lib = load_library()
+        self.path = path
+        self._checked = set()
+
+    # -- helpers ---------------------------------------------------------------------------------
+    def _prep(self, *tensors):
+        dev = tensors[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("mamba_clip_b200 kernels need CUDA tensors (no CPU fallback); got " + str(dev))
+        if dev.index not in self._checked:
+            sm = ctypes.c_int(0)
+            _check(self.lib, self.lib.mclip_device_supported(dev.index if dev.index is not None else torch.cuda.current_device(),
+                                                             ctypes.byref(sm)), "mclip_device_supported")
+            self._checked.add(dev.index)
+        for t in tensors:
+            if t is not None and t.device != dev:
+                raise ValueError("all tensors must be on the same device")
+        return dev
+
+    def _stream(self, dev):
+        return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+    def _workspace(self, M, N, D, dtype, op, dev):
+        n = ctypes.c_size_t(0)
+        _check(self.lib, self.lib.mclip_workspace_bytes(M, N, D, DTYPE_CODES[dtype], op, self.path, ctypes.byref(n)),
+               "mclip_workspace_bytes")
+        if n.value == 0:
+            return None, 0
+        return torch.empty(n.value, dtype=torch.uint8, device=dev), n.value
+
+    def launch_count(self) -> int:
+        return int(self.lib.mclip_launch_count())
+
+    # -- ops -------------------------------------------------------------------------------------
+    def row_lse(self, X: torch.Tensor, Y: torch.Tensor, ls: torch.Tensor, diag_off: int,
+                want_diag: bool) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+        dev = self._prep(X, Y, ls)
+        M, D = X.shape
+        N = Y.shape[0]
+        lse = torch.empty(M, dtype=torch.float32, device=dev)
+        diag = torch.empty(M, dtype=torch.float32, device=dev) if want_diag else None
+        ws, nws = self._workspace(M, N, D, X.dtype, OP_ROW_LSE, dev)
+        with torch.cuda.device(dev):
+            rc = self.lib.mclip_row_lse(_ptr(X), _ptr(Y), M, N, D, X.stride(0), Y.stride(0), DTYPE_CODES[X.dtype],
+                                        _ptr(ls), diag_off, _ptr(lse), _ptr(diag), _ptr(ws), nws, self.path,
+                                        self._stream(dev))
+        _check(self.lib, rc, "mclip_row_lse")
+        return lse, diag
+
+    def block_grad(self, X, Y, ls, go, lse_x, lse_y, diag_off, w_row, w_col, w_diag, inv_2n, want_rowdot=True):
+        dev = self._prep(X, Y, ls, lse_x)
+        M, D = X.shape
+        N = Y.shape[0]
+        dX = torch.empty((M, D), dtype=X.dtype, device=dev)
+        rowdot = torch.empty(M, dtype=torch.float32, device=dev) if want_rowdot else None
+        ws, nws = self._workspace(M, N, D, X.dtype, OP_BLOCK_GRAD, dev)
+        with torch.cuda.device(dev):
+            rc = self.lib.mclip_block_grad(_ptr(X), _ptr(Y), M, N, D, X.stride(0), Y.stride(0), DTYPE_CODES[X.dtype],
+                                           _ptr(ls), _ptr(go), _ptr(lse_x), _ptr(lse_y), diag_off, w_row, w_col,
+                                           w_diag, inv_2n, _ptr(dX), dX.stride(0), _ptr(rowdot), _ptr(ws), nws,
+                                           self.path, self._stream(dev))
+        _check(self.lib, rc, "mclip_block_grad")
+        return dX, rowdot
+
+    def loss_finalize(self, row_lse, col_lse, diag, ls):
+        dev = self._prep(row_lse, col_lse, diag, ls)
+        out = torch.empty((), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = self.lib.mclip_loss_finalize(_ptr(row_lse), _ptr(col_lse), _ptr(diag), row_lse.numel(), _ptr(ls),
+                                              _ptr(out), self._stream(dev))
+        _check(self.lib, rc, "mclip_loss_finalize")
+        return out
+
+    def dls_finalize(self, u, v, diag, go, scale):
+        dev = self._prep(u, v, diag)
+        out = torch.empty(2, dtype=torch.float32, device=dev)
+        t_out, dls_out = out[0:1], out[1:2]
+        with torch.cuda.device(dev):
+            rc = self.lib.mclip_dls_finalize(_ptr(u), _ptr(v), _ptr(diag), u.numel(), _ptr(go), float(scale),
+                                             _ptr(t_out), _ptr(dls_out), self._stream(dev))
+        _check(self.lib, rc, "mclip_dls_finalize")
+        return out[0], out[1]
+
+
+_backend = None
+_override = None
+
+
+def set_backend_override(obj):
+    """Test hook: route the four primitive ops to `obj` (None restores the CUDA library)."""
+    global _override
+    _override = obj
+
+
+def get_backend():
+    global _backend
+    if _override is not None:
+        return _override
+    if _backend is None:
+        _backend = CudaBackend()
+    return _backend

@@ -1,0 +1,166 @@
+"""Autograd Function + collective plumbing behind `ClipLoss.forward`.
+
+The reference builds this with implicit autograd over `logit_scale * a @ b.T` and
+`F.cross_entropy` (reference src/mamba_clip/loss.py:89-113,142-145) and torch's `_AllGather`.
+Here the forward is two calls of the fused row-LSE kernel and the backward two calls of the fused
+recompute kernel; see DESIGN.md for the decomposition:
+
+  rank r owns rows R of S = ls * I T^T (block "I_r x all T") and columns R of S (block "T_r x all I").
+  forward : row_lse[R] from the first block, col_lse[R] + diag from the second -> loss_r
+  exchange: features are all-gathered once (NCCL, contiguous buffers); for the modes whose gradient has
+            cross terms the two O(B) LSE vectors are all-gathered as well (8*B_l bytes per rank)
+  backward: dI_r and dT_r are each complete on the owning rank -> no gradient collective at all; only
+            `local_loss=False` needs one scalar all-reduce for d(logit_scale).
+Per-rank values reproduce the reference exactly, including the W x factors.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import _cabi
+
+_SUPPORTED = (torch.float32, torch.bfloat16, torch.float16)
+
+
+def _gather_rows(x: torch.Tensor, world_size: int, group) -> torch.Tensor:
+    """All-gather `[B_l, ...]` shards into one contiguous `[W*B_l, ...]` buffer (no list + cat copy)."""
+    out = torch.empty((world_size * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    try:
+        dist.all_gather_into_tensor(out, x.contiguous(), group=group)
+    except (RuntimeError, NotImplementedError):  # backends without the flat variant
+        dist.all_gather(list(out.chunk(world_size, dim=0)), x.contiguous(), group=group)
+    return out
+
+
+def _compute_dtype(t: torch.Tensor) -> torch.dtype:
+    """dtype the kernels run in.  Inside an autocast region fp32 features are rounded to the autocast
+    dtype, which is what the reference's `@` does there; otherwise the input dtype."""
+    if t.dtype == torch.float32 and t.is_cuda and torch.is_autocast_enabled():
+        ac = torch.get_autocast_gpu_dtype()
+        if ac in (torch.bfloat16, torch.float16):
+            return ac
+    if t.dtype in _SUPPORTED:
+        return t.dtype
+    return torch.float32
+
+
+class ClipLossFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, image_features, text_features, logit_scale, local_loss, gather_with_grad, rank, world_size,
+                group):
+        be = _cabi.get_backend()
+        dev = image_features.device
+        cdt = _compute_dtype(image_features)
+        xi = image_features.detach().to(cdt).contiguous()
+        xt = text_features.detach().to(cdt).contiguous()
+        if torch.is_tensor(logit_scale):
+            ls = logit_scale.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
+        else:
+            ls = torch.full((1,), float(logit_scale), dtype=torch.float32, device=dev)
+        W = int(world_size)
+        Bl = xi.shape[0]
+        if W > 1:
+            all_i = _gather_rows(xi, W, group)
+            all_t = _gather_rows(xt, W, group)
+            off = int(rank) * Bl
+        else:
+            all_i, all_t, off = xi, xt, 0
+
+        row_lse, diag = be.row_lse(xi, all_t, ls, off, True)     # rows R of S
+        col_lse, _ = be.row_lse(xt, all_i, ls, off, False)       # columns R of S
+        loss = be.loss_finalize(row_lse, col_lse, diag, ls)      # the rank's local loss
+        if W > 1 and not local_loss:
+            # reference: one global [B_g, B_g] problem on every rank == mean of the equal-sized rank losses
+            dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
+            loss = loss / W
+
+        own_terms_only = W > 1 and local_loss and not gather_with_grad
+        if W > 1 and not own_terms_only:
+            stats = _gather_rows(torch.stack((row_lse, col_lse)).unsqueeze(0), W, group)  # [W, 2, B_l]
+            row_lse_all = stats[:, 0, :].reshape(-1).contiguous()
+            col_lse_all = stats[:, 1, :].reshape(-1).contiguous()
+        elif own_terms_only:
+            row_lse_all = col_lse_all = None
+        else:
+            row_lse_all, col_lse_all = row_lse, col_lse
+
+        ctx.save_for_backward(xi, xt, all_i, all_t, ls, row_lse, col_lse, diag,
+                              row_lse_all if row_lse_all is not None else row_lse,
+                              col_lse_all if col_lse_all is not None else col_lse)
+        ctx.cfg = (bool(local_loss), bool(gather_with_grad), W, off, own_terms_only, group)
+        ctx.in_dtypes = (image_features.dtype, text_features.dtype)
+        ctx.ls_meta = (logit_scale.dtype, logit_scale.shape, logit_scale.device) if torch.is_tensor(logit_scale) else None
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        be = _cabi.get_backend()
+        xi, xt, all_i, all_t, ls, row_lse, col_lse, diag, row_lse_all, col_lse_all = ctx.saved_tensors
+        local_loss, gather_with_grad, W, off, own_terms_only, group = ctx.cfg
+        Bl = xi.shape[0]
+        Bg = W * Bl
+        go = grad_out.detach().to(device=xi.device, dtype=torch.float32).reshape(1).contiguous()
+
+        # 1/(2n) of the feature gradients: the true gradient for W=1 and (False, False),
+        # W x that otherwise.
+        n_feat = Bg if (W == 1 or (not local_loss and not gather_with_grad)) else Bl
+        inv_2n = 1.0 / (2.0 * n_feat)
+        if own_terms_only:
+            w_row, w_col, w_diag = 1.0, 0.0, 1.0
+            lse_y_i = lse_y_t = None
+        else:
+            w_row, w_col, w_diag = 1.0, 1.0, 2.0
+            lse_y_i, lse_y_t = col_lse_all, row_lse_all
+
+        need_i, need_t, need_ls = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        d_img = d_txt = d_ls = None
+        u = v = None
+        if need_i or need_ls:
+            d_img, u = be.block_grad(xi, all_t, ls, go, row_lse, lse_y_i, off, w_row, w_col, w_diag, inv_2n)
+        if need_t or need_ls:
+            d_txt, v = be.block_grad(xt, all_i, ls, go, col_lse, lse_y_t, off, w_row, w_col, w_diag, inv_2n)
+        if need_ls and ctx.ls_meta is not None:
+            n_ls = Bl if (W > 1 and local_loss) else Bg
+            t, d_ls = be.dls_finalize(u, v, diag, go, 1.0 / (2.0 * n_ls))
+            if W > 1 and not local_loss:
+                t = t.clone()
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+                d_ls = go[0] * t / (2.0 * n_ls)
+            dt, shape, dev = ctx.ls_meta
+            d_ls = d_ls.reshape(shape).to(device=dev, dtype=dt)
+        else:
+            d_ls = None
+        if d_img is not None:
+            d_img = d_img.to(ctx.in_dtypes[0]) if need_i else None
+        if d_txt is not None:
+            d_txt = d_txt.to(ctx.in_dtypes[1]) if need_t else None
+        return d_img, d_txt, d_ls, None, None, None, None, None
+
+
+def clip_loss(image_features: torch.Tensor, text_features: torch.Tensor, logit_scale, local_loss: bool = False,
+              gather_with_grad: bool = False, rank: int = 0, world_size: int = 1, group=None) -> torch.Tensor:
+    """Functional form with the argument validation the reference leaves to torch errors / hangs."""
+    if image_features.dim() != 2 or text_features.dim() != 2:
+        raise ValueError(f"features must be [B, D]; got {tuple(image_features.shape)} and {tuple(text_features.shape)}")
+    if image_features.shape != text_features.shape:
+        raise ValueError(f"image/text feature shapes differ: {tuple(image_features.shape)} vs {tuple(text_features.shape)}")
+    if image_features.device != text_features.device:
+        raise ValueError("image_features and text_features are on different devices")
+    if image_features.shape[0] == 0 or image_features.shape[1] == 0:
+        raise ValueError("empty batch")
+    if torch.is_tensor(logit_scale) and logit_scale.numel() != 1:
+        raise ValueError("logit_scale must be a scalar")
+    world_size = int(world_size)
+    if world_size > 1:
+        if not dist.is_available() or not dist.is_initialized():
+            raise RuntimeError("world_size > 1 needs an initialised torch.distributed process group")
+        pg = dist.get_world_size(group)
+        if pg != world_size:
+            raise ValueError(f"world_size={world_size} does not match the process group size {pg}")
+        if not (0 <= int(rank) < world_size):
+            raise ValueError(f"rank {rank} outside [0, {world_size})")
+    return ClipLossFunction.apply(image_features, text_features, logit_scale, bool(local_loss),
+                                  bool(gather_with_grad), int(rank), world_size, group)

@@ -1,0 +1,139 @@
+// extern "C" boundary of libmclip_b200.so (see include/mclip_b200.h for the contract).
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace mclip {
+
+static thread_local char g_err[512] = {0};
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+  return MCLIP_ERR_CUDA;
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+static bool valid_dtype(int d) { return d == MCLIP_DTYPE_F32 || d == MCLIP_DTYPE_BF16 || d == MCLIP_DTYPE_F16; }
+
+static int check_common(const void* X, const void* Y, int64_t M, int64_t N, int64_t D, int64_t ldx,
+                        int64_t ldy, int dtype, const float* ls, int path, const char* op) {
+  if (!X || !Y || !ls) { set_error("%s: null pointer (X=%p Y=%p logit_scale=%p)", op, X, Y, (const void*)ls); return MCLIP_ERR_INVALID; }
+  if (M <= 0 || N <= 0 || D <= 0) { set_error("%s: empty problem M=%lld N=%lld D=%lld", op, (long long)M, (long long)N, (long long)D); return MCLIP_ERR_INVALID; }
+  if (M > (1ll << 30) || N > (1ll << 30) || D > (1ll << 20)) { set_error("%s: problem too large", op); return MCLIP_ERR_INVALID; }
+  if (ldx < D || ldy < D) { set_error("%s: leading dimension smaller than D (ldx=%lld ldy=%lld D=%lld)", op, (long long)ldx, (long long)ldy, (long long)D); return MCLIP_ERR_INVALID; }
+  if (!valid_dtype(dtype)) { set_error("%s: bad dtype %d", op, dtype); return MCLIP_ERR_INVALID; }
+  if (path != MCLIP_PATH_AUTO && path != MCLIP_PATH_SIMT && path != MCLIP_PATH_TCGEN05) { set_error("%s: bad path %d", op, path); return MCLIP_ERR_INVALID; }
+  return MCLIP_OK;
+}
+
+static int resolve_path(int64_t M, int64_t N, int64_t D, int64_t ldx, int64_t ldy, int dtype, int op, int path,
+                        const char* name, int* out) {
+  const bool tc = tc_supported(M, N, D, ldx, ldy, dtype, op);
+  if (path == MCLIP_PATH_TCGEN05 && !tc) {
+    set_error("%s: tcgen05 path cannot run this problem (needs bf16/f16, D %% 8 == 0, D <= 768, ld %% 8 == 0)", name);
+    return MCLIP_ERR_UNSUPPORTED;
+  }
+  *out = (path == MCLIP_PATH_AUTO) ? (tc ? MCLIP_PATH_TCGEN05 : MCLIP_PATH_SIMT) : path;
+  return MCLIP_OK;
+}
+
+}  // namespace mclip
+
+using namespace mclip;
+
+extern "C" {
+
+int mclip_abi_version(void) { return MCLIP_ABI_VERSION; }
+
+const char* mclip_last_error(void) { return g_err; }
+
+int64_t mclip_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int mclip_device_supported(int device, int* sm) {
+  cudaDeviceProp p;
+  MCLIP_CUDA_OK(cudaGetDeviceProperties(&p, device));
+  if (sm) *sm = p.major * 10 + p.minor;
+  if (p.major != 10) {
+    set_error("device %d is sm_%d%d; libmclip_b200 is built for sm_100a only", device, p.major, p.minor);
+    return MCLIP_ERR_UNSUPPORTED;
+  }
+  return MCLIP_OK;
+}
+
+int mclip_select_path(int64_t M, int64_t N, int64_t D, int64_t ldx, int64_t ldy, int dtype, int op) {
+  return tc_supported(M, N, D, ldx, ldy, dtype, op) ? MCLIP_PATH_TCGEN05 : MCLIP_PATH_SIMT;
+}
+
+int mclip_workspace_bytes(int64_t M, int64_t N, int64_t D, int dtype, int op, int path, size_t* bytes) {
+  if (!bytes || M <= 0 || N <= 0 || D <= 0 || !valid_dtype(dtype)) { set_error("workspace_bytes: invalid argument"); return MCLIP_ERR_INVALID; }
+  // AUTO callers may not know leading dims yet: size for the larger of the two paths.
+  size_t simt = 0, tc = 0;
+  if (op == MCLIP_OP_ROW_LSE) { simt = simt_row_lse_ws(M, N, D); tc = tc_row_lse_ws(M, N, D); }
+  else if (op == MCLIP_OP_BLOCK_GRAD) { simt = simt_block_grad_ws(M, N, D); tc = tc_block_grad_ws(M, N, D); }
+  else { set_error("workspace_bytes: bad op %d", op); return MCLIP_ERR_INVALID; }
+  if (path == MCLIP_PATH_SIMT) *bytes = simt;
+  else if (path == MCLIP_PATH_TCGEN05) *bytes = tc;
+  else *bytes = simt > tc ? simt : tc;
+  return MCLIP_OK;
+}
+
+int mclip_row_lse(const void* X, const void* Y, int64_t M, int64_t N, int64_t D, int64_t ldx, int64_t ldy,
+                  int dtype, const float* logit_scale, int64_t diag_off, float* lse, float* diag, void* ws,
+                  size_t ws_bytes, int path, void* cuda_stream) {
+  int rc = check_common(X, Y, M, N, D, ldx, ldy, dtype, logit_scale, path, "row_lse");
+  if (rc) return rc;
+  if (!lse) { set_error("row_lse: lse is null"); return MCLIP_ERR_INVALID; }
+  int p;
+  rc = resolve_path(M, N, D, ldx, ldy, dtype, MCLIP_OP_ROW_LSE, path, "row_lse", &p);
+  if (rc) return rc;
+  const size_t need = (p == MCLIP_PATH_TCGEN05) ? tc_row_lse_ws(M, N, D) : simt_row_lse_ws(M, N, D);
+  if (need > 0 && (!ws || ws_bytes < need)) { set_error("row_lse: workspace %zu < %zu bytes", ws_bytes, need); return MCLIP_ERR_WORKSPACE; }
+  RowLseArgs a{X, Y, M, N, D, ldx, ldy, dtype, logit_scale, diag_off, lse, diag, ws, ws_bytes, (cudaStream_t)cuda_stream};
+  return (p == MCLIP_PATH_TCGEN05) ? tc_row_lse(a) : simt_row_lse(a);
+}
+
+int mclip_block_grad(const void* X, const void* Y, int64_t M, int64_t N, int64_t D, int64_t ldx, int64_t ldy,
+                     int dtype, const float* logit_scale, const float* grad_out, const float* lse_x,
+                     const float* lse_y, int64_t diag_off, float w_row, float w_col, float w_diag, float inv_2n,
+                     void* dX, int64_t lddx, float* rowdot, void* ws, size_t ws_bytes, int path, void* cuda_stream) {
+  int rc = check_common(X, Y, M, N, D, ldx, ldy, dtype, logit_scale, path, "block_grad");
+  if (rc) return rc;
+  if (!lse_x || !dX) { set_error("block_grad: null lse_x/dX"); return MCLIP_ERR_INVALID; }
+  if (w_col != 0.f && !lse_y) { set_error("block_grad: w_col != 0 needs lse_y"); return MCLIP_ERR_INVALID; }
+  if (lddx < D) { set_error("block_grad: lddx < D"); return MCLIP_ERR_INVALID; }
+  int p;
+  // dX shares X's alignment requirements on the tcgen05 path
+  rc = resolve_path(M, N, D, ldx | lddx, ldy, dtype, MCLIP_OP_BLOCK_GRAD, path, "block_grad", &p);
+  if (rc) return rc;
+  const size_t need = (p == MCLIP_PATH_TCGEN05) ? tc_block_grad_ws(M, N, D) : simt_block_grad_ws(M, N, D);
+  if (need > 0 && (!ws || ws_bytes < need)) { set_error("block_grad: workspace %zu < %zu bytes", ws_bytes, need); return MCLIP_ERR_WORKSPACE; }
+  BlockGradArgs a{X, Y, M, N, D, ldx, ldy, dtype, logit_scale, grad_out, lse_x, lse_y, diag_off,
+                  w_row, w_col, w_diag, inv_2n, dX, lddx, rowdot, ws, ws_bytes, (cudaStream_t)cuda_stream};
+  return (p == MCLIP_PATH_TCGEN05) ? tc_block_grad(a) : simt_block_grad(a);
+}
+
+int mclip_loss_finalize(const float* row_lse, const float* col_lse, const float* diag, int64_t n,
+                        const float* logit_scale, float* loss, void* cuda_stream) {
+  if (!row_lse || !col_lse || !diag || !logit_scale || !loss || n <= 0) { set_error("loss_finalize: invalid argument"); return MCLIP_ERR_INVALID; }
+  return launch_loss_finalize(row_lse, col_lse, diag, n, logit_scale, loss, (cudaStream_t)cuda_stream);
+}
+
+int mclip_dls_finalize(const float* u, const float* v, const float* diag, int64_t n, const float* grad_out,
+                       float scale, float* t_out, float* dls_out, void* cuda_stream) {
+  if (!u || !v || !diag || !t_out || !dls_out || n <= 0) { set_error("dls_finalize: invalid argument"); return MCLIP_ERR_INVALID; }
+  return launch_dls_finalize(u, v, diag, n, grad_out, scale, t_out, dls_out, (cudaStream_t)cuda_stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,78 @@
+"""The C-ABI shared library: builds for sm_100a, loads without a GPU, exports every symbol that
+include/mclip_b200.h declares, and rejects bad arguments with error codes (no compute calls here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from mamba_clip_b200 import _cabi, build
+    build.build()
+    return _cabi.load_library()
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "mclip_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mclip_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_header_symbols_are_exported_and_bound(lib):
+    from mamba_clip_b200 import _cabi
+    names = declared_symbols()
+    assert len(names) >= 10
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/mclip_b200.h but not exported"
+    assert sorted(_cabi.EXPORTED_SYMBOLS) == names
+    assert lib.mclip_abi_version() == _cabi.ABI_VERSION
+
+
+def test_no_torch_or_libcuda_link_dependency():
+    import subprocess
+    out = subprocess.run(["ldd", os.path.join(ROOT, "mamba_clip_b200", "libmclip_b200.so")],
+                         capture_output=True, text=True).stdout
+    assert "libtorch" not in out and "libc10" not in out
+    assert "libcuda.so" not in out  # driver entry points are resolved at run time
+
+
+def test_argument_validation_without_gpu(lib):
+    n = ctypes.c_size_t(0)
+    assert lib.mclip_workspace_bytes(128, 128, 64, 1, 0, 0, ctypes.byref(n)) == 0
+    assert lib.mclip_workspace_bytes(0, 128, 64, 1, 0, 0, ctypes.byref(n)) == 1
+    assert lib.mclip_workspace_bytes(128, 128, 64, 7, 0, 0, ctypes.byref(n)) == 1
+    assert b"invalid" in lib.mclip_last_error()
+    # null pointers -> MCLIP_ERR_INVALID before any CUDA call
+    rc = lib.mclip_row_lse(None, None, 4, 4, 8, 8, 8, 0, None, 0, None, None, None, 0, 0, None)
+    assert rc == 1 and b"null" in lib.mclip_last_error()
+    rc = lib.mclip_block_grad(None, None, 4, 4, 8, 8, 8, 0, None, None, None, None, 0, 1.0, 1.0, 2.0, 0.5,
+                              None, 8, None, None, 0, 0, None)
+    assert rc == 1
+    assert lib.mclip_loss_finalize(None, None, None, 4, None, None, None) == 1
+    assert lib.mclip_dls_finalize(None, None, None, 4, None, 1.0, None, None, None) == 1
+
+
+def test_path_selection(lib):
+    TC, SIMT = 2, 1
+    assert lib.mclip_select_path(4096, 4096, 512, 512, 512, 1, 0) == TC      # bf16, D=512
+    assert lib.mclip_select_path(4096, 4096, 512, 512, 512, 2, 1) == TC      # f16
+    assert lib.mclip_select_path(4096, 4096, 512, 512, 512, 0, 0) == SIMT    # fp32 needs fp32 math (1e-5 bar)
+    assert lib.mclip_select_path(64, 64, 100, 100, 100, 1, 0) == SIMT        # D % 8 != 0
+    assert lib.mclip_select_path(64, 64, 1024, 1024, 1024, 1, 0) == SIMT     # D > 768
+    assert lib.mclip_select_path(64, 64, 768, 768, 768, 1, 0) == TC
+
+
+def test_sass_has_blackwell_instructions():
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    sass = subprocess.run(["cuobjdump", "-sass", os.path.join(ROOT, "mamba_clip_b200", "libmclip_b200.so")],
+                          capture_output=True, text=True).stdout
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "STTM"):
+        assert mnemonic in sass, f"{mnemonic} missing from SASS"
+    assert "HMMA.16816" not in sass  # no legacy mma.sync path

@@ -1,0 +1,267 @@
+"""GPU parity tests proper: the CUDA kernels, called through the C ABI, against the CPU oracle on the
+same seeded inputs.  fp32 inputs (FFMA path): <= 1e-5 relative.  bf16/f16 inputs (tcgen05 path):
+<= 2e-3 relative against the oracle run on the fp32 upcast of the same 16-bit values."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import clip_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TOL = {torch.float32: 1e-5, torch.bfloat16: 2e-3, torch.float16: 2e-3}
+
+
+def backend(path):
+    from mamba_clip_b200 import _cabi
+    return _cabi.CudaBackend(path=path)
+
+
+def feats(M, N, D, dtype, seed, correlated=False, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.nn.functional.normalize(torch.randn(M, D, generator=g), dim=-1) * scale
+    y = torch.nn.functional.normalize(torch.randn(N, D, generator=g), dim=-1) * scale
+    if correlated:
+        k = min(M, N)
+        y[:k] = torch.nn.functional.normalize(x[:k] + 0.1 * torch.randn(k, D, generator=g), dim=-1) * scale
+    return x.to(dtype), y.to(dtype)
+
+
+SIMT, TC = 1, 2
+ROW_LSE_CASES = [
+    # (path, dtype, M, N, D, ls, diag_off)
+    (SIMT, torch.float32, 1, 1, 8, 5.0, 0),
+    (SIMT, torch.float32, 7, 100, 33, 14.2857, 3),
+    (SIMT, torch.float32, 64, 64, 512, 14.2857, 0),
+    (SIMT, torch.float32, 129, 257, 512, 100.0, 64),
+    (SIMT, torch.float32, 300, 2000, 768, 100.0, 1000),
+    (SIMT, torch.bfloat16, 100, 333, 100, 30.0, 7),
+    (SIMT, torch.float16, 65, 129, 1032, 30.0, 0),
+    (SIMT, torch.float32, 64, 640, 64, -7.5, 0),          # negative scale is legal for a float logit_scale
+    (TC, torch.bfloat16, 64, 64, 64, 14.2857, 0),
+    (TC, torch.bfloat16, 128, 256, 512, 14.2857, 0),
+    (TC, torch.bfloat16, 129, 300, 512, 100.0, 64),
+    (TC, torch.bfloat16, 1, 1, 8, 5.0, 0),
+    (TC, torch.bfloat16, 200, 1000, 200, 30.0, 400),
+    (TC, torch.float16, 300, 1000, 768, 30.0, 17),
+    (TC, torch.bfloat16, 512, 4096, 512, 100.0, 1024),
+    (TC, torch.bfloat16, 384, 5000, 256, -12.0, 0),
+    (TC, torch.bfloat16, 2048, 2048, 512, 14.2857, 0),
+]
+
+
+def _ids(cases):
+    return [("simt" if c[0] == SIMT else "tc") + "-" + str(c[1]).split(".")[-1] + "-" + "x".join(str(v) for v in c[2:5])
+            for c in cases]
+
+
+@pytest.mark.parametrize("path,dtype,M,N,D,ls,diag_off", ROW_LSE_CASES, ids=_ids(ROW_LSE_CASES))
+def test_row_lse(path, dtype, M, N, D, ls, diag_off):
+    be = backend(path)
+    x, y = feats(M, N, D, dtype, seed=M * 7 + N, correlated=True)
+    xd, yd = x.cuda(), y.cuda()
+    lsd = torch.tensor([ls], dtype=torch.float32, device="cuda")
+    lse, diag = be.row_lse(xd, yd, lsd, diag_off, True)
+    torch.cuda.synchronize()
+    ref_lse, ref_diag = O.block_row_lse(x.float(), y.float(), ls, diag_off)
+    tol = TOL[dtype]
+    # LSE is compared absolutely relative to the logit magnitude it is a statistic of
+    assert float((lse.cpu().double() - ref_lse).abs().max()) <= tol * max(1.0, abs(ls)) * 0.5 + 2e-6
+    assert float((diag.cpu().double() - ref_diag).abs().max()) <= 2e-6
+    lse2, none = be.row_lse(xd, yd, lsd, diag_off, False)
+    assert none is None and torch.equal(lse2, lse)       # deterministic, diag optional
+
+
+def test_row_lse_strided_rows():
+    """leading dimension > D (a column slice of a wider matrix) on both paths."""
+    for path, dtype in ((SIMT, torch.float32), (TC, torch.bfloat16)):
+        be = backend(path)
+        x, y = feats(130, 270, 256, dtype, seed=5)
+        xw = torch.zeros(130, 320, dtype=dtype, device="cuda")
+        yw = torch.zeros(270, 264, dtype=dtype, device="cuda")
+        xw[:, :256] = x.cuda()
+        yw[:, :256] = y.cuda()
+        lsd = torch.tensor([20.0], device="cuda")
+        lse, _ = be.row_lse(xw[:, :256], yw[:, :256], lsd, 0, True)
+        ref, _ = O.block_row_lse(x.float(), y.float(), 20.0, 0)
+        assert float((lse.cpu().double() - ref).abs().max()) <= TOL[dtype] * 10
+
+
+GRAD_CASES = [
+    # (path, dtype, M, N, D, ls, diag_off, (w_row, w_col, w_diag))
+    (SIMT, torch.float32, 1, 1, 8, 5.0, 0, (1, 1, 2)),
+    (SIMT, torch.float32, 7, 100, 33, 14.2857, 3, (1, 1, 2)),
+    (SIMT, torch.float32, 64, 64, 512, 14.2857, 0, (1, 1, 2)),
+    (SIMT, torch.float32, 129, 257, 512, 30.0, 64, (1, 0, 1)),
+    (SIMT, torch.float32, 100, 700, 768, 100.0, 300, (1, 1, 2)),
+    (SIMT, torch.bfloat16, 100, 333, 100, 30.0, 7, (1, 1, 2)),
+    (TC, torch.bfloat16, 64, 64, 64, 14.2857, 0, (1, 1, 2)),
+    (TC, torch.bfloat16, 128, 128, 512, 14.2857, 0, (1, 1, 2)),
+    (TC, torch.bfloat16, 128, 256, 256, 14.2857, 0, (1, 0, 1)),
+    (TC, torch.bfloat16, 129, 300, 512, 30.0, 64, (1, 1, 2)),
+    (TC, torch.bfloat16, 1, 1, 8, 5.0, 0, (1, 1, 2)),
+    (TC, torch.bfloat16, 200, 1000, 200, 30.0, 400, (1, 1, 2)),
+    (TC, torch.float16, 300, 1000, 768, 30.0, 17, (1, 1, 2)),
+    (TC, torch.bfloat16, 512, 4096, 512, 100.0, 1024, (1, 1, 2)),
+    (TC, torch.bfloat16, 256, 3000, 384, 14.2857, 0, (1, 0, 1)),
+    (TC, torch.bfloat16, 2048, 2048, 512, 14.2857, 0, (1, 1, 2)),
+]
+
+
+@pytest.mark.parametrize("path,dtype,M,N,D,ls,diag_off,w", GRAD_CASES, ids=_ids(GRAD_CASES))
+def test_block_grad(path, dtype, M, N, D, ls, diag_off, w):
+    be = backend(path)
+    x, y = feats(M, N, D, dtype, seed=M * 3 + N, correlated=True)
+    xf, yf = x.float(), y.float()
+    lse_x, _ = O.block_row_lse(xf, yf, ls, None)
+    lse_y, _ = O.block_row_lse(yf, xf, ls, None)          # column LSE of the same block
+    go, inv_2n = 3.0, 1.0 / (2 * M)
+    ref_dx, ref_rd = O.block_grad(xf, yf, ls, lse_x, lse_y, diag_off, *w, alpha=go * ls * inv_2n)
+    dev = "cuda"
+    dx, rd = be.block_grad(x.to(dev), y.to(dev), torch.tensor([ls], device=dev), torch.tensor([go], device=dev),
+                           lse_x.float().to(dev), lse_y.float().to(dev) if w[1] else None, diag_off,
+                           float(w[0]), float(w[1]), float(w[2]), inv_2n)
+    torch.cuda.synchronize()
+    assert dx.dtype == dtype and dx.shape == (M, D)
+    tol = TOL[dtype]
+    scale = go * abs(ls) * inv_2n * M ** 0.5            # natural size of dX for unit-norm rows
+    err = float((dx.cpu().double() - ref_dx).norm())
+    assert err <= tol * float(ref_dx.norm()) + 4 * 1.2e-7 * max(1.0, abs(ls)) * scale
+    assert float((rd.cpu().double() - ref_rd).abs().max()) <= (1e-5 if dtype == torch.float32 else 2e-3) * max(
+        1.0, float(ref_rd.abs().max()))
+
+
+def load_single():
+    z = np.load(os.path.join(GOLD, "single.npz"))
+    return z, json.loads(str(z["cases"]))
+
+
+def projector(dim):
+    g = torch.Generator().manual_seed(4242)
+    return torch.randn(dim, 8, generator=g, dtype=torch.float64)
+
+
+Z, CASES = load_single()
+
+
+@pytest.mark.parametrize("k", range(len(CASES)))
+def test_clip_loss_against_reference_golden(k):
+    """ClipLoss (W=1) on the GPU vs the outputs of the real reference ClipLoss (tests/golden)."""
+    from mamba_clip_b200 import ClipLoss
+    case = CASES[k]
+    img, txt = O.make_features(case["B"], case["D"], seed=case["seed"], correlated=case["corr"])
+    dtype = torch.bfloat16 if case["bf16"] else torch.float32
+    img = img.to(dtype).cuda().requires_grad_(True)
+    txt = txt.to(dtype).cuda().requires_grad_(True)
+    ls = torch.tensor(case["ls"], device="cuda", requires_grad=True)
+    loss = ClipLoss(cache_labels=True)(image_features=img, text_features=txt, logit_scale=ls, target=None)["contrastive_loss"]
+    loss.backward(torch.tensor(case["go"], device="cuda"))
+    tol = TOL[dtype]
+    gl, gd = float(Z[f"c{k}_loss"]), float(Z[f"c{k}_dls"])
+    assert loss.dtype == torch.float32 and img.grad.dtype == dtype
+    assert abs(float(loss.detach()) - gl) <= tol * max(abs(gl), 1e-3 if case["bf16"] else 1.0) + 3e-6
+    assert abs(float(ls.grad) - gd) <= max(tol, 3e-5) * abs(gd) + 1.2e-7 * case["go"] * max(1.0, case["ls"]) * (
+        20 if case["bf16"] else 1)
+    B = case["B"]
+    floor = 4 * 1.2e-7 * max(1.0, case["ls"]) * case["go"] * case["ls"] / (2 * B) * B ** 0.5
+    if case["bf16"]:
+        floor *= 50   # G is rounded to bf16 before the MMA: absolute floor ~2^-9 of |G| <= 2
+    for key, g in (("di", img.grad), ("dt", txt.grad)):
+        g = g.detach().cpu().double()
+        if f"c{k}_{key}_full" in Z:
+            ref = torch.from_numpy(Z[f"c{k}_{key}_full"]).double()
+            assert float((g - ref).norm()) <= tol * float(ref.norm()) + floor
+        else:
+            ref = torch.from_numpy(Z[f"c{k}_{key}_proj"])
+            assert float((g @ projector(g.shape[1]) - ref).norm()) <= tol * float(ref.norm()) + 8 * floor
+
+
+@pytest.mark.parametrize("B,D,dtype,ls", [(4096, 512, torch.bfloat16, 14.2857), (4096, 512, torch.bfloat16, 100.0),
+                                          (3000, 768, torch.float16, 30.0), (1024, 512, torch.float32, 100.0)])
+def test_clip_loss_medium_against_closed_form(B, D, dtype, ls):
+    from mamba_clip_b200 import ClipLoss
+    img, txt = O.make_features(B, D, seed=99, correlated=True, dtype=dtype)
+    ref = O.closed_form(img.float(), txt.float(), ls, 1, 0, False, False, grad_output=2.0)
+    a = img.cuda().requires_grad_(True)
+    b = txt.cuda().requires_grad_(True)
+    s = torch.tensor(ls, device="cuda", requires_grad=True)
+    loss = ClipLoss()(a, b, s, output_dict=False)
+    loss.backward(torch.tensor(2.0, device="cuda"))
+    tol = TOL[dtype]
+    assert abs(float(loss.detach()) - float(ref.loss)) <= tol * abs(float(ref.loss)) + 3e-6
+    assert O.rel_err(a.grad.cpu(), ref.d_image) <= tol
+    assert O.rel_err(b.grad.cpu(), ref.d_text) <= tol
+    assert abs(float(s.grad) - float(ref.d_logit_scale)) <= max(tol, 3e-5) * abs(float(ref.d_logit_scale)) + 1e-6
+
+
+def test_symmetry_and_homogeneity_properties():
+    """Size-independent properties: swapping image/text swaps the gradients; Euler homogeneity
+    sum_i <I_i, dI_i> = sum_j <T_j, dT_j> = ls * d(ls)."""
+    from mamba_clip_b200 import ClipLoss
+    img, txt = O.make_features(1536, 512, seed=11, correlated=True, dtype=torch.bfloat16)
+    outs = []
+    for a0, b0 in ((img, txt), (txt, img)):
+        a = a0.cuda().requires_grad_(True)
+        b = b0.cuda().requires_grad_(True)
+        s = torch.tensor(25.0, device="cuda", requires_grad=True)
+        loss = ClipLoss()(a, b, s, output_dict=False)
+        loss.backward()
+        outs.append((float(loss.detach()), a.grad.float(), b.grad.float(), float(s.grad), a.detach().float(), b.detach().float()))
+    (l0, di0, dt0, ds0, a0, b0), (l1, di1, dt1, ds1, _, _) = outs
+    assert abs(l0 - l1) <= 1e-6 * abs(l0) and abs(ds0 - ds1) <= 1e-5 * abs(ds0) + 1e-9
+    assert torch.equal(di0, dt1) and torch.equal(dt0, di1)
+    e_i = float((a0 * di0).sum())
+    e_t = float((b0 * dt0).sum())
+    assert abs(e_i - 25.0 * ds0) <= 4e-3 * abs(25.0 * ds0) + 1e-6
+    assert abs(e_t - 25.0 * ds0) <= 4e-3 * abs(25.0 * ds0) + 1e-6
+
+
+def test_autocast_rounds_fp32_features_like_the_reference_matmul():
+    from mamba_clip_b200 import ClipLoss
+    img, txt = O.make_features(256, 512, seed=21, correlated=True)
+    a = img.cuda().requires_grad_(True)
+    b = txt.cuda().requires_grad_(True)
+    s = torch.tensor(14.2857, device="cuda", requires_grad=True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        loss = ClipLoss()(a, b, s)["contrastive_loss"]
+    loss.backward()
+    assert loss.dtype == torch.float32 and a.grad.dtype == torch.float32
+    ref = O.closed_form(img.bfloat16().float(), txt.bfloat16().float(), 14.2857, 1, 0, False, False)
+    assert abs(float(loss.detach()) - float(ref.loss)) <= 2e-3 * abs(float(ref.loss))
+    assert O.rel_err(a.grad.cpu(), ref.d_image) <= 2e-3
+
+
+def test_grad_only_where_required():
+    from mamba_clip_b200 import ClipLoss
+    img, txt = O.make_features(64, 64, seed=1)
+    a = img.cuda().requires_grad_(True)
+    loss = ClipLoss()(a, txt.cuda(), 10.0, output_dict=False)
+    loss.backward()
+    assert a.grad is not None
+    with torch.no_grad():
+        l2 = ClipLoss()(img.cuda(), txt.cuda(), torch.tensor(10.0, device="cuda"), output_dict=False)
+    assert abs(float(l2) - float(loss.detach())) < 1e-6
+
+
+def test_error_paths_on_gpu():
+    from mamba_clip_b200 import ClipLoss, _cabi
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ClipLoss()(torch.randn(4, 8), torch.randn(4, 8), torch.tensor(1.0))
+    be = _cabi.CudaBackend(path=2)
+    x = torch.randn(8, 12, device="cuda")
+    with pytest.raises(RuntimeError, match="tcgen05 path cannot run"):
+        be.row_lse(x, x, torch.ones(1, device="cuda"), 0, False)   # fp32 cannot be forced onto tensor cores
+
+
+def test_launch_counter_moves():
+    from mamba_clip_b200 import ClipLoss, _cabi
+    be = _cabi.get_backend()
+    n0 = be.launch_count()
+    img, txt = O.make_features(64, 64, seed=1, dtype=torch.bfloat16)
+    a = img.cuda().requires_grad_(True)
+    ClipLoss()(a, txt.cuda(), torch.tensor(10.0, device="cuda"), output_dict=False).backward()
+    assert be.launch_count() - n0 >= 6

@@ -1,0 +1,190 @@
+"""Host-side logic of ClipLoss (mode algebra, gathers, scalar reductions) on CPU: the C-ABI primitives are
+replaced by their oracle statements (tests/_emul.py) and the result is compared with the golden vectors
+of the real reference, single process and 2/4-rank gloo."""
+import json
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import clip_oracle as O
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+SINGLE = np.load(os.path.join(GOLD, "single.npz"))
+RANKS = np.load(os.path.join(GOLD, "ranks.npz"))
+SINGLE_CASES = json.loads(str(SINGLE["cases"]))
+RANK_CASES = json.loads(str(RANKS["cases"]))
+
+
+def grad_floor(go, ls, n):
+    """Absolute noise floor of a feature gradient: the row/column LSE is carried between forward and
+    backward as one fp32 number of magnitude ~ls, so P = exp(s - lse) has ~eps*max(1, ls) relative error;
+    times the gradient's natural scale go*ls/(2n)*sqrt(n) (unit-norm rows).  Only matters for saturated
+    softmaxes (ls = 100, correlated pairs) where the reference gradient itself is rounding noise."""
+    return 4 * 1.2e-7 * max(1.0, ls) * go * ls / (2 * n) * n ** 0.5
+
+
+@pytest.fixture()
+def emulated():
+    from mamba_clip_b200 import _cabi
+    from tests._emul import EmulatedBackend
+    be = EmulatedBackend()
+    _cabi.set_backend_override(be)
+    yield be
+    _cabi.set_backend_override(None)
+
+
+def test_api_surface_matches_reference():
+    import inspect
+    import mamba_clip_b200.loss as L
+    sig = inspect.signature(L.ClipLoss.__init__)
+    assert list(sig.parameters)[1:] == ["local_loss", "gather_with_grad", "cache_labels", "rank", "world_size"]
+    assert [p.default for p in list(sig.parameters.values())[1:]] == [False, False, False, 0, 1]
+    fsig = inspect.signature(L.ClipLoss.forward)
+    assert list(fsig.parameters)[1:] == ["image_features", "text_features", "logit_scale", "output_dict", "target"]
+    crit = L.ClipLoss()
+    assert isinstance(crit, torch.nn.Module) and len(crit.state_dict()) == 0
+    for attr in ("local_loss", "gather_with_grad", "cache_labels", "rank", "world_size", "prev_num_logits", "labels"):
+        assert hasattr(crit, attr)
+    for fn in ("create_loss", "all_gather", "cross_entropy_loss"):
+        assert callable(getattr(L, fn))
+
+    class A:
+        local_loss, gather_with_grad, rank, world_size = True, True, 3, 8
+    c = L.create_loss(A)
+    assert (c.local_loss, c.gather_with_grad, c.cache_labels, c.rank, c.world_size) == (True, True, True, 3, 8)
+    # labels helper behaves like loss.py:76-87
+    lab = c.get_ground_truth(torch.device("cpu"), 4)
+    assert lab.tolist() == [12, 13, 14, 15] and c.prev_num_logits == 4
+
+
+def test_cross_entropy_loss_matches_torch():
+    from mamba_clip_b200.loss import cross_entropy_loss
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(16, 2, generator=g)
+    y = torch.randint(0, 2, (16,), generator=g)
+    assert torch.allclose(cross_entropy_loss(x, y), torch.nn.functional.cross_entropy(x, y))
+    soft = torch.softmax(torch.randn(16, 2, generator=g), -1)
+    assert torch.allclose(cross_entropy_loss(x, soft), -(x.log_softmax(-1) * soft).sum(-1).mean())
+
+
+def test_validation_errors(emulated):
+    from mamba_clip_b200 import ClipLoss
+    crit = ClipLoss()
+    with pytest.raises(ValueError):
+        crit(torch.randn(4, 8), torch.randn(5, 8), torch.tensor(1.0))
+    with pytest.raises(ValueError):
+        crit(torch.randn(4, 8, 2), torch.randn(4, 8, 2), torch.tensor(1.0))
+    with pytest.raises(ValueError):
+        crit(torch.randn(0, 8), torch.randn(0, 8), torch.tensor(1.0))
+    with pytest.raises(RuntimeError):
+        ClipLoss(world_size=2)(torch.randn(4, 8), torch.randn(4, 8), torch.tensor(1.0))
+
+
+def test_cpu_tensors_raise_without_override():
+    from mamba_clip_b200 import ClipLoss
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ClipLoss()(torch.randn(4, 8), torch.randn(4, 8), torch.tensor(1.0))
+
+
+@pytest.mark.parametrize("k", [k for k, c in enumerate(SINGLE_CASES) if c["B"] <= 129])
+def test_single_process_against_golden(emulated, k):
+    from mamba_clip_b200 import ClipLoss
+    case = SINGLE_CASES[k]
+    img, txt = O.make_features(case["B"], case["D"], seed=case["seed"], correlated=case["corr"])
+    if case["bf16"]:
+        img, txt = img.bfloat16().float(), txt.bfloat16().float()
+    img.requires_grad_(True)
+    txt.requires_grad_(True)
+    ls = torch.tensor(case["ls"], requires_grad=True)
+    out = ClipLoss(cache_labels=True)(image_features=img, text_features=txt, logit_scale=ls, target=None)
+    assert set(out) == {"contrastive_loss"}
+    loss = out["contrastive_loss"]
+    loss.backward(torch.tensor(case["go"]))
+    gl, gd = float(SINGLE[f"c{k}_loss"]), float(SINGLE[f"c{k}_dls"])
+    assert abs(float(loss.detach()) - gl) <= 3e-6 * max(1.0, abs(gl)) + 2e-7
+    # LSE is stored in fp32: |lse| ~ ls, so P carries ~eps*ls relative error and d(ls) an absolute floor
+    assert abs(float(ls.grad) - gd) <= 3e-5 * abs(gd) + 1.2e-7 * case["go"] * max(1.0, case["ls"])
+    floor = grad_floor(case["go"], case["ls"], case["B"])
+    for key, g in (("di", img.grad), ("dt", txt.grad)):
+        gn = float(SINGLE[f"c{k}_{key}_norm"])
+        assert abs(float(g.double().norm()) - gn) <= 2e-5 * gn + floor
+        if f"c{k}_{key}_full" in SINGLE:
+            ref = torch.from_numpy(SINGLE[f"c{k}_{key}_full"]).double()
+            assert float((g.double() - ref).norm()) <= 2e-5 * float(ref.norm()) + floor
+    assert emulated.calls.count("row_lse") == 2 and emulated.calls.count("block_grad") == 2
+
+
+def test_output_dict_false_and_float_scale(emulated):
+    from mamba_clip_b200 import ClipLoss
+    img, txt = O.make_features(16, 32, seed=3)
+    img.requires_grad_(True)
+    a = ClipLoss()(img, txt, 10.0, output_dict=False)
+    assert a.dim() == 0
+    a.backward()
+    ref = O.ref_port_single(img.detach(), txt, 10.0)
+    assert abs(float(a) - float(ref.loss)) < 1e-5
+    assert O.rel_err(img.grad, ref.d_image) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------
+# multi-process gloo
+# ---------------------------------------------------------------------------------------------------
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, case, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=case["W"])
+    try:
+        from mamba_clip_b200 import ClipLoss, _cabi
+        from tests._emul import EmulatedBackend
+        _cabi.set_backend_override(EmulatedBackend())
+        W, Bl = case["W"], case["Bl"]
+        img, txt = O.make_features(W * Bl, case["D"], seed=case["seed"], correlated=case["corr"])
+        img = img[rank * Bl:(rank + 1) * Bl].clone().requires_grad_(True)
+        txt = txt[rank * Bl:(rank + 1) * Bl].clone().requires_grad_(True)
+        ls = torch.tensor(case["ls"], requires_grad=True)
+        crit = ClipLoss(case["local_loss"], case["gwg"], True, rank, W)
+        loss = crit(img, txt, ls)["contrastive_loss"]
+        loss.backward(torch.tensor(case["go"]))
+        q.put((rank, float(loss), img.grad.numpy(), txt.grad.numpy(), float(ls.grad)))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("k", range(len(RANK_CASES)))
+def test_gloo_ranks_against_golden(k):
+    case = RANK_CASES[k]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, case, port, q)) for r in range(case["W"])]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=180) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    Bl = case["Bl"]
+    floor = grad_floor(case["go"], case["ls"], Bl)
+    for rank, loss, di, dt, dls in res:
+        gl = float(RANKS[f"c{k}_r{rank}_loss"])
+        gd = float(RANKS[f"c{k}_r{rank}_dls"])
+        gi = torch.from_numpy(RANKS[f"c{k}_r{rank}_di"]).double()
+        gt = torch.from_numpy(RANKS[f"c{k}_r{rank}_dt"]).double()
+        assert abs(loss - gl) <= 3e-6 * max(1.0, abs(gl)) + 2e-7
+        assert abs(dls - gd) <= 3e-5 * abs(gd) + 1.2e-7 * case["go"] * max(1.0, case["ls"])
+        assert float((torch.from_numpy(di).double() - gi).norm()) <= 2e-5 * float(gi.norm()) + floor
+        assert float((torch.from_numpy(dt).double() - gt).norm()) <= 2e-5 * float(gt.norm()) + floor
