@@ -1,0 +1,111 @@
+"""Multi-GPU (NCCL) parity of ClipLoss: one process per GPU, all four (local_loss, gather_with_grad) modes,
+against the golden vectors of the real reference run under gloo and, at tensor-core sizes, against the
+single-process rank emulation of the oracle.  Skipped when fewer than 2 GPUs are visible."""
+import json
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import clip_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _ngpu():
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, W, port, jobs, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=W, device_id=dev)
+    try:
+        from mamba_clip_b200 import ClipLoss
+        for j, job in enumerate(jobs):
+            Bl, D = job["Bl"], job["D"]
+            dtype = getattr(torch, job["dtype"])
+            img, txt = O.make_features(W * Bl, D, seed=job["seed"], correlated=job["corr"], dtype=dtype)
+            a = img[rank * Bl:(rank + 1) * Bl].to(dev).requires_grad_(True)
+            b = txt[rank * Bl:(rank + 1) * Bl].to(dev).requires_grad_(True)
+            ls = torch.tensor(job["ls"], device=dev, requires_grad=True)
+            crit = ClipLoss(job["local_loss"], job["gwg"], True, rank, W)
+            loss = crit(a, b, ls)["contrastive_loss"]
+            loss.backward(torch.tensor(job["go"], device=dev))
+            q.put((j, rank, float(loss.detach()), a.grad.float().cpu().numpy(), b.grad.float().cpu().numpy(), float(ls.grad)))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(W, jobs):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, W, port, jobs, q)) for r in range(W)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in range(W * len(jobs))]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    return {(j, r): rest for j, r, *rest in res}
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
+def test_nccl_two_ranks_against_reference_golden():
+    Z = np.load(os.path.join(GOLD, "ranks.npz"))
+    cases = json.loads(str(Z["cases"]))
+    ks = [k for k, c in enumerate(cases) if c["W"] == 2]
+    jobs = [dict(cases[k], dtype="float32") for k in ks]
+    out = _run(2, jobs)
+    for j, k in enumerate(ks):
+        c = cases[k]
+        floor = 4 * 1.2e-7 * max(1.0, c["ls"]) * c["go"] * c["ls"] / (2 * c["Bl"]) * c["Bl"] ** 0.5
+        for r in range(2):
+            loss, di, dt, dls = out[(j, r)]
+            gl, gd = float(Z[f"c{k}_r{r}_loss"]), float(Z[f"c{k}_r{r}_dls"])
+            gi = torch.from_numpy(Z[f"c{k}_r{r}_di"]).double()
+            gt = torch.from_numpy(Z[f"c{k}_r{r}_dt"]).double()
+            assert abs(loss - gl) <= 1e-5 * max(1.0, abs(gl))
+            assert abs(dls - gd) <= 3e-5 * abs(gd) + 1.2e-7 * c["go"] * max(1.0, c["ls"])
+            assert float((torch.from_numpy(di).double() - gi).norm()) <= 1e-5 * float(gi.norm()) + floor
+            assert float((torch.from_numpy(dt).double() - gt).norm()) <= 1e-5 * float(gt.norm()) + floor
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("W", [2, 4, 8])
+def test_nccl_bf16_tensor_core_sizes_against_oracle(W):
+    if _ngpu() < W:
+        pytest.skip(f"needs {W} GPUs")
+    jobs = []
+    for local_loss in (False, True):
+        for gwg in (False, True):
+            jobs.append(dict(Bl=256, D=512, dtype="bfloat16", seed=77, corr=True, ls=20.0, go=2.0,
+                             local_loss=local_loss, gwg=gwg))
+    out = _run(W, jobs)
+    for j, job in enumerate(jobs):
+        img, txt = O.make_features(W * 256, 512, seed=77, correlated=True, dtype=torch.bfloat16)
+        ref = O.ref_port_ranks(img.float(), txt.float(), 20.0, W, job["local_loss"], job["gwg"], grad_output=2.0)
+        for r in range(W):
+            loss, di, dt, dls = out[(j, r)]
+            assert abs(loss - float(ref[r].loss)) <= 2e-3 * abs(float(ref[r].loss)) + 1e-6
+            assert O.rel_err(torch.from_numpy(di), ref[r].d_image) <= 2e-3
+            assert O.rel_err(torch.from_numpy(dt), ref[r].d_text) <= 2e-3
+            assert abs(dls - float(ref[r].d_logit_scale)) <= 2e-3 * abs(float(ref[r].d_logit_scale)) + 1e-7

@@ -131,8 +131,9 @@ def test_block_grad(path, dtype, M, N, D, ls, diag_off, w):
     scale = go * abs(ls) * inv_2n * M ** 0.5            # natural size of dX for unit-norm rows
     err = float((dx.cpu().double() - ref_dx).norm())
     assert err <= tol * float(ref_dx.norm()) + 4 * 1.2e-7 * max(1.0, abs(ls)) * scale
-    assert float((rd.cpu().double() - ref_rd).abs().max()) <= (1e-5 if dtype == torch.float32 else 2e-3) * max(
-        1.0, float(ref_rd.abs().max()))
+    # rowdot = sum_j P_ij c_ij: P inherits the fp32 rounding of s = ls * c (|s| up to ls), i.e. ~eps * ls relative
+    rd_tol = (4 * 1.2e-7 * max(1.0, abs(ls)) + 1e-6) if dtype == torch.float32 else 2e-3
+    assert float((rd.cpu().double() - ref_rd).abs().max()) <= rd_tol * max(1.0, float(ref_rd.abs().max()))
 
 
 def load_single():
