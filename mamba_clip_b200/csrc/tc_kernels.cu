@@ -10,6 +10,8 @@
 // warps 4..11 = epilogue (two warpgroups; warp w reads TMEM lanes 32*(w%4).. and one column half).
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 
@@ -58,7 +60,8 @@ struct BwdParams {
   float w_row, w_col, w_diag, inv_2n;
   void* dX;
   int64_t lddx;
-  float* acc_ws;        // f32 [M, D] when nsplit > 1
+  float* acc_ws;        // f32 [nsplit][M, D] partial dX when nsplit > 1 (summed in fixed order afterwards)
+  float* rd_ws;         // f32 [nsplit][M] partial rowdot when nsplit > 1
   float* rowdot;
 };
 
@@ -162,7 +165,7 @@ tc_row_lse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   } else if (warp == 1) {
     if (lane == 0) {
       // ---------------- MMA issuer ----------------
-      const uint32_t idesc = make_idesc_f16(p.bf16 != 0, 128, BN, false, false);
+      const uint32_t idesc = make_idesc_f16(p.bf16 != 0, p.bf16 != 0, 128, BN, false, false);
       if (XRES) mbar_wait(xfull_bar, 0);
       uint32_t it = 0;
       for (int lt = 0; lt < ntiles; ++lt) {
@@ -260,7 +263,7 @@ tc_row_lse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 // TMEM columns: S/G buffers [0,128) and [128,256); dX accumulator [256, 512).
 // G (16-bit, two per column) overwrites its own S buffer: warpgroup 0 owns S columns [0,64) -> G columns
 // [0,32); warpgroup 1 owns S columns [64,128) -> G columns [64,96).
-template <bool kBF16, bool kMasked, bool kCol>
+template <bool kGBF16, bool kMasked, bool kCol>
 __device__ __forceinline__ void bwd_chunk(const uint32_t (&v)[32], uint32_t (&g)[16], float k2, float lx2,
                                           const float* __restrict__ ly2, float lw_diag, int64_t col0, int64_t N,
                                           int64_t jd, float& rd) {
@@ -280,11 +283,13 @@ __device__ __forceinline__ void bwd_chunk(const uint32_t (&v)[32], uint32_t (&g)
       rd = fmaf(p_row, c, rd);
       gv[e] = gg;
     }
-    g[j >> 1] = kBF16 ? pack_bf16x2(gv[0], gv[1]) : pack_f16x2(gv[0], gv[1]);
+    g[j >> 1] = kGBF16 ? pack_bf16x2(gv[0], gv[1]) : pack_f16x2(gv[0], gv[1]);
   }
 }
 
-template <bool kBF16, bool XRES>
+// Single-CTA version (any D <= 768; used for D > 512).  kGF16: G is written as f16 scaled by 2^12; only legal when
+// Y is f16 too (tcgen05 kind::f16 raises an illegal-instruction fault for A = f16, B = bf16 -- measured).
+template <bool kBF16, bool XRES, bool kGF16>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_block_grad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -371,8 +376,8 @@ tc_block_grad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   } else if (warp == 1) {
     if (lane == 0) {
       // ---------------- MMA issuer ----------------
-      const uint32_t idesc_s = make_idesc_f16(kBF16, 128, 128, false, false);
-      const uint32_t idesc_dx = make_idesc_f16(kBF16, 128, (uint32_t)ndc * 64, false, true);
+      const uint32_t idesc_s = make_idesc_f16(kBF16, kBF16, 128, 128, false, false);
+      const uint32_t idesc_dx = make_idesc_f16(kBF16 && !kGF16, kBF16, 128, (uint32_t)ndc * 64, false, true);
       if (XRES) mbar_wait(xfull_bar, 0);
       uint32_t it = 0;
       auto issue_s = [&](int ls_) {
@@ -434,8 +439,12 @@ tc_block_grad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     const float k2 = ls * kLog2e;
     const bool has_col = p.w_col != 0.f;
     // weights folded into the exponents: w * 2^a = 2^(a + log2 w)
-    const float lw_row = log2f(p.w_row);
-    const float lw_col = has_col ? log2f(p.w_col) : 0.f;
+    constexpr bool kGBF16 = kBF16 && !kGF16;
+    constexpr float kGShift = kGF16 ? 12.f : 0.f;      // G is stored as G * 2^kGShift
+    constexpr float kGScale = kGF16 ? 4096.f : 1.f;
+    const float lw_row = log2f(p.w_row) + kGShift;
+    const float lw_col = (has_col ? log2f(p.w_col) : 0.f) + kGShift;
+    const float w_diag_s = p.w_diag * kGScale;
     const float lx2 = (row < p.M ? p.lse_x[row] * kLog2e : 0.f) - lw_row;
     const int64_t jd = row + p.diag_off;
     float rd = 0.f;
@@ -463,11 +472,11 @@ tc_block_grad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         const float* ly2 = ly2_s + buf * 128 + cbase;
         const int64_t col0 = n0 + cbase;
         if (special) {
-          if (has_col) bwd_chunk<kBF16, true, true>(v, g, k2, lx2, ly2, p.w_diag, col0, p.N, jd, rd);
-          else bwd_chunk<kBF16, true, false>(v, g, k2, lx2, ly2, p.w_diag, col0, p.N, jd, rd);
+          if (has_col) bwd_chunk<kGBF16, true, true>(v, g, k2, lx2, ly2, w_diag_s, col0, p.N, jd, rd);
+          else bwd_chunk<kGBF16, true, false>(v, g, k2, lx2, ly2, w_diag_s, col0, p.N, jd, rd);
         } else {
-          if (has_col) bwd_chunk<kBF16, false, true>(v, g, k2, lx2, ly2, p.w_diag, col0, p.N, jd, rd);
-          else bwd_chunk<kBF16, false, false>(v, g, k2, lx2, ly2, p.w_diag, col0, p.N, jd, rd);
+          if (has_col) bwd_chunk<kGBF16, false, true>(v, g, k2, lx2, ly2, w_diag_s, col0, p.N, jd, rd);
+          else bwd_chunk<kGBF16, false, false>(v, g, k2, lx2, ly2, w_diag_s, col0, p.N, jd, rd);
         }
         tmem_st16(lane_addr + buf * 128 + half * 64 + cc * 16, g);
       }
@@ -479,7 +488,7 @@ tc_block_grad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     // ---- dX accumulator -> global ----
     mbar_wait(dxfull_bar, 0);
     tc_fence_after();
-    const float alpha = (p.go ? p.go[0] : 1.f) * ls * p.inv_2n;
+    const float alpha = (p.go ? p.go[0] : 1.f) * ls * p.inv_2n * (1.f / kGScale);
     const int ncc = ndc;  // 32-column chunks per warpgroup: (ndc * 64 / 2) / 32
     for (int cc = 0; cc < ncc; ++cc) {
       uint32_t v[32];
@@ -489,10 +498,17 @@ tc_block_grad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       const int64_t d0 = (int64_t)dc0 * 64 + cbase;
       if (row < p.M && nsteps > 0) {
         if (p.nsplit > 1) {
-          float* dst = p.acc_ws + row * p.D + d0;
+          // this split's partial (unscaled, f32); summed over splits in fixed order by acc_to_dx_kernel
+          float* dst = p.acc_ws + ((int64_t)blockIdx.z * p.M + row) * p.D + d0;
+          if (d0 + 32 <= p.D) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (d0 + j < p.D) atomicAdd(dst + j, __uint_as_float(v[j]));
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<uint4*>(dst + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (d0 + j < p.D) dst[j] = __uint_as_float(v[j]);
+          }
         } else if (d0 + 32 <= p.D) {
           uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.dX) + row * p.lddx + d0);
 #pragma unroll
@@ -520,7 +536,17 @@ tc_block_grad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         }
       }
     }
-    if (p.rowdot != nullptr && blockIdx.y == 0 && row < p.M) atomicAdd(p.rowdot + row, rd);
+    // rowdot: add the two column halves through shared memory (fixed order), one value per row and split
+    if (p.rowdot != nullptr && blockIdx.y == 0) {
+      named_bar_sync(1, kEpiThreads);            // everyone is done with ly2_s
+      if (half == 1) ly2_s[row_in_tile] = rd;
+      named_bar_sync(1, kEpiThreads);
+      if (half == 0 && row < p.M) {
+        const float tot = (rd + ly2_s[row_in_tile]) * (1.f / kGScale);
+        if (p.nsplit > 1) p.rd_ws[(int64_t)blockIdx.z * p.M + row] = tot;
+        else p.rowdot[row] = tot;
+      }
+    }
   }
 
   tc_fence_before();
@@ -531,15 +557,417 @@ tc_block_grad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   }
 }
 
-// f32 accumulation workspace -> dX (split-y mode)
+// per-split f32 partials -> dX (and rowdot), summed in split order: deterministic, no atomics
 template <typename T>
-__global__ void acc_to_dx_kernel(const float* __restrict__ acc, int64_t M, int64_t D, const float* __restrict__ ls,
-                                 const float* __restrict__ go, float inv_2n, T* __restrict__ dX, int64_t lddx) {
-  const float alpha = (go ? go[0] : 1.f) * ls[0] * inv_2n;
+__global__ void acc_to_dx_kernel(const float* __restrict__ acc, const float* __restrict__ rd_ws, int nsplit, int64_t M,
+                                 int64_t D, const float* __restrict__ ls, const float* __restrict__ go, float scale,
+                                 T* __restrict__ dX, int64_t lddx, float* __restrict__ rowdot) {
+  const float alpha = (go ? go[0] : 1.f) * ls[0] * scale;
   const int64_t n = M * D;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = tid * 4; i < n; i += nth * 4) {   // D % 8 == 0 on this path, so a float4 never straddles rows
+    float4 a = *reinterpret_cast<const float4*>(acc + i);
+    for (int s = 1; s < nsplit; ++s) {
+      const float4 b = *reinterpret_cast<const float4*>(acc + (int64_t)s * n + i);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
     const int64_t r = i / D, d = i - r * D;
-    dX[r * lddx + d] = from_f32<T>(acc[i] * alpha);
+    T* o = dX + r * lddx + d;
+    o[0] = from_f32<T>(a.x * alpha); o[1] = from_f32<T>(a.y * alpha);
+    o[2] = from_f32<T>(a.z * alpha); o[3] = from_f32<T>(a.w * alpha);
+  }
+  if (rowdot != nullptr) {
+    for (int64_t i = tid; i < M; i += nth) {
+      float t = rd_ws[i];
+      for (int s = 1; s < nsplit; ++s) t += rd_ws[(int64_t)s * M + i];
+      rowdot[i] = t;
+    }
+  }
+}
+
+
+// =================================================================================================
+// backward, CTA-pair version (D <= 512): no second S recompute
+// =================================================================================================
+// A cluster of two CTAs owns 128 rows of X (64 per CTA) and issues cta_group::2 MMAs with M = 128.  In that
+// shape each CTA's accumulator holds 64 rows with the N columns folded over the two lane halves (lanes 0-63:
+// columns [0, N/2), lanes 64-127: [N/2, N)), so the whole dX block [64 x 512] f32 takes only 256 TMEM columns
+// per CTA and still leaves room for two S buffers [64 x 256] (128 columns each).  Per 256-row step of Y:
+//   S  = X Y^T        M=128 N=256 K=D      A: resident X tiles (K-major), B: Y tiles, N split over the pair
+//   G  = f(S)         epilogue warps, f16 * 2^12, written to shared memory as the next A operand (K-major, SW128)
+//   dX += G Y16       M=128 N=256 (x2 halves of D) K=256   B: Y16 tiles read MN-major, N split over the pair
+// All Y traffic streams through one ring of 32 KB stages (two [128 x 64] tiles each).
+struct Bwd2Params {
+  int64_t M, N, D;
+  int kpairs;           // ceil(ceil(D/64) / 2): S stages per step
+  int ndh;              // ceil(D / 256): 256-wide halves of D
+  int steps_total;      // ceil(N / 256)
+  int steps_per_split;
+  int nsplit;
+  int64_t diag_off;
+  const float* ls;
+  const float* go;
+  const float* lse_x;
+  const float* ly2;     // [steps_total * 256] lse_y in log2 units, weight and G scale folded, +inf padded; null if w_col == 0
+  float w_row, w_diag, inv_2n;
+  int has_col;
+  void* dX;
+  int64_t lddx;
+  float* acc_ws;
+  float* rd_ws;
+  float* rowdot;
+};
+
+constexpr uint32_t kTile8K = 64 * 64 * 2;     // [64 rows x 64 k]
+constexpr uint32_t kStage2 = 2 * kChunkBytes; // ring stage: two [128 x 64] tiles
+constexpr int kRing2 = 3;
+constexpr float kGScale = 4096.f;             // G is stored as G * 2^12 in f16
+
+template <bool kMasked, bool kCol>
+__device__ __forceinline__ void bwd2_chunk(const uint32_t (&v)[32], uint32_t (&g)[16], float k2, float lx2,
+                                           const float* __restrict__ ly2, float w_diag_s, int64_t col0, int64_t N,
+                                           int64_t jd, float& rd) {
+  float ly[32];
+  if (kCol) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(ly2 + j));
+      ly[j] = t.x; ly[j + 1] = t.y; ly[j + 2] = t.z; ly[j + 3] = t.w;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    float gv[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const float c = __uint_as_float(v[j + e]);
+      float p_row = ex2_approx(fmaf(c, k2, -lx2));
+      float gg = p_row;
+      if (kCol) gg += ex2_approx(fmaf(c, k2, -ly[j + e]));
+      if (kMasked) {
+        if (col0 + j + e == jd) gg -= w_diag_s;
+        if (col0 + j + e >= N) { gg = 0.f; p_row = 0.f; }
+      }
+      rd = fmaf(p_row, c, rd);
+      gv[e] = gg;
+    }
+    g[j >> 1] = pack_f16x2(gv[0], gv[1]);
+  }
+}
+
+template <bool kBF16>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
+                      const __grid_constant__ CUtensorMap tmY16, const Bwd2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = align1024(smem_u32(smem_raw));
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t x_base = smem_base;                              // [8][64 rows][64 k]   64 KB
+  const uint32_t g_base = x_base + 8 * kTile8K;                   // [2][4][64 rows][64 y] 64 KB
+  const uint32_t ring_base = g_base + 2 * 4 * kTile8K;            // [kRing2][2][128][64]  96 KB
+  const uint32_t misc_base = ring_base + kRing2 * kStage2;
+  uint8_t* misc_gen = smem_gen + (misc_base - smem_base);
+  const uint32_t bar_base = misc_base;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };             // leader: both CTAs' TMA bytes
+  auto empty_bar = [&](int s) { return bar_base + 8u * (4 + s); };      // per CTA, MMA commit multicast
+  const uint32_t xfull_bar = bar_base + 8u * 8;                          // leader
+  auto sfull_bar = [&](int b) { return bar_base + 8u * (9 + b); };      // per CTA, multicast
+  auto gfull_bar = [&](int b) { return bar_base + 8u * (11 + b); };     // leader: 16 epilogue warps
+  auto gempty_bar = [&](int b) { return bar_base + 8u * (13 + b); };    // per CTA, multicast
+  const uint32_t dxfull_bar = bar_base + 8u * 15;                        // per CTA, multicast
+  const uint32_t tmem_slot = bar_base + 8u * 16;
+  uint32_t* tmem_slot_gen = reinterpret_cast<uint32_t*>(misc_gen + 8u * 16);
+  float* rd_scratch = reinterpret_cast<float*>(misc_gen + 256);          // [4][64]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int64_t m0 = (int64_t)(blockIdx.x >> 1) * 128 + 64 * rank;   // this CTA's 64 rows
+  const int s0 = blockIdx.y * p.steps_per_split;
+  const int s1 = min(p.steps_total, s0 + p.steps_per_split);
+  const int nsteps = s1 - s0;
+  constexpr uint32_t kTmemCols = 512;
+  constexpr uint32_t kDxCol = 256;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmY);
+    tma_prefetch_desc(&tmY16);
+    for (int s = 0; s < kRing2; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
+    mbar_init(xfull_bar, 2);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(sfull_bar(b), 1);
+      mbar_init(gfull_bar(b), 2 * (kEpiThreads / 32));
+      mbar_init(gempty_bar(b), 1);
+    }
+    mbar_init(dxfull_bar, 1);
+    fence_barrier_init();
+  } else if (warp == 2) {
+    tmem_alloc_cg2(tmem_slot, kTmemCols);
+    tmem_relinquish_cg2();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer (both CTAs; bytes are credited to the leader's barriers) ----------------
+      if (leader) mbar_expect_tx(xfull_bar, 2 * 8 * kTile8K); else mbar_arrive_cluster(xfull_bar, 0);
+      for (int c = 0; c < 8; ++c) tma_load_2d_cg2(x_base + c * kTile8K, &tmX, c * 64, (int32_t)m0, xfull_bar);
+      uint32_t it = 0;
+      auto stage_begin = [&]() -> uint32_t {
+        const int s = it % kRing2;
+        const uint32_t ph = (it / kRing2) & 1;
+        mbar_wait(empty_bar(s), ph ^ 1);
+        if (leader) mbar_expect_tx(full_bar(s), 2 * kStage2); else mbar_arrive_cluster(full_bar(s), 0);
+        ++it;
+        return (uint32_t)s;
+      };
+      auto load_s = [&](int st) {   // Y tiles of step st as the N operand of S: this CTA's 128 rows, all of D
+        const int32_t y0 = (s0 + st) * 256 + 128 * (int32_t)rank;
+        for (int i = 0; i < p.kpairs; ++i) {
+          const uint32_t s = stage_begin();
+          const uint32_t dst = ring_base + s * kStage2;
+          tma_load_2d_cg2(dst, &tmY, (2 * i) * 64, y0, full_bar(s));
+          tma_load_2d_cg2(dst + kChunkBytes, &tmY, (2 * i + 1) * 64, y0, full_bar(s));
+        }
+      };
+      auto load_dx = [&](int st) {  // Y16 tiles of step st as the [K = y][N = d] operand of dX: all 256 rows, this CTA's d
+        for (int yh = 0; yh < 2; ++yh) {
+          const int32_t y0 = (s0 + st) * 256 + 128 * yh;
+          for (int h = 0; h < p.ndh; ++h) {
+            const uint32_t s = stage_begin();
+            const uint32_t dst = ring_base + s * kStage2;
+            const int32_t dcol = (4 * h + 2 * (int32_t)rank) * 64;
+            tma_load_2d_cg2(dst, &tmY16, dcol, y0, full_bar(s));
+            tma_load_2d_cg2(dst + kChunkBytes, &tmY16, dcol + 64, y0, full_bar(s));
+          }
+        }
+      };
+      if (nsteps > 0) load_s(0);
+      for (int st = 0; st < nsteps; ++st) {
+        if (st + 1 < nsteps) load_s(st + 1);
+        load_dx(st);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      // ---------------- MMA issuer (leader CTA only) ----------------
+      const uint32_t idesc_s = make_idesc_f16(kBF16, kBF16, 128, 256, false, false);
+      const uint32_t idesc_dx = make_idesc_f16(false, false, 128, 256, false, true);
+      mbar_wait(xfull_bar, 0);
+      uint32_t it = 0;
+      auto stage_wait = [&]() -> uint32_t {
+        const int s = it % kRing2;
+        const uint32_t ph = (it / kRing2) & 1;
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        ++it;
+        return (uint32_t)s;
+      };
+      auto issue_s = [&](int st) {
+        const int buf = st & 1;
+        // S buffer `buf` was last read by the epilogue of step st-2, whose gfull arrival the dX issue of that step
+        // has already waited for; nothing more to wait on here.
+        const uint32_t d_tmem = tmem_base + buf * 128;
+        for (int i = 0; i < p.kpairs; ++i) {
+          const uint32_t s = stage_wait();
+          const uint32_t b_addr = ring_base + s * kStage2;
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t ad = make_smem_desc_sw128(x_base + (2 * i + e) * kTile8K + k * 32, 0, 1024);
+              const uint64_t bd = make_smem_desc_sw128(b_addr + e * kChunkBytes + k * 32, 0, 1024);
+              mma_ss_cg2(d_tmem, ad, bd, idesc_s, (i | e | k) != 0);
+            }
+          }
+          mma_commit_cg2(empty_bar(s), 3);
+        }
+        mma_commit_cg2(sfull_bar(buf), 3);
+      };
+      auto issue_dx = [&](int st) {
+        const int buf = st & 1;
+        const uint32_t bph = (st >> 1) & 1;
+        mbar_wait(gfull_bar(buf), bph);
+        tc_fence_after();
+        for (int yh = 0; yh < 2; ++yh) {
+          for (int h = 0; h < p.ndh; ++h) {
+            const uint32_t s = stage_wait();
+            const uint32_t b_addr = ring_base + s * kStage2;
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+              // A = G[64 rows x 16 y] of K-chunk (2*yh + kk/4); B = Y16[16 y][128 d per CTA], MN-major
+              const uint64_t ad = make_smem_desc_sw128(g_base + (buf * 4 + 2 * yh + (kk >> 2)) * kTile8K + (kk & 3) * 32, 0, 1024);
+              const uint64_t bd = make_smem_desc_sw128(b_addr + kk * 2048, kChunkBytes, 1024);
+              mma_ss_cg2(tmem_base + kDxCol + h * 128, ad, bd, idesc_dx, (st | yh | kk) != 0);
+            }
+            mma_commit_cg2(empty_bar(s), 3);
+          }
+        }
+        mma_commit_cg2(gempty_bar(buf), 3);
+      };
+      if (nsteps > 0) issue_s(0);
+      for (int st = 0; st < nsteps; ++st) {
+        if (st + 1 < nsteps) issue_s(st + 1);
+        issue_dx(st);
+      }
+      mma_commit_cg2(dxfull_bar, 3);
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ---------------- epilogue: S -> G (f16 * 2^12) into shared memory; finally dX out ----------------
+    const int ew = warp - kEpiWarp0;
+    const int q = warp & 3;                   // TMEM lane quadrant
+    const int half = ew >> 2;                 // which 64 of this lane-half's 128 columns
+    const int r = (q & 1) * 32 + lane;        // row within this CTA's 64
+    const int cS = (q >> 1) * 128 + half * 64;   // first S column (of 256) this thread handles
+    const int kc = cS >> 6;                   // K-chunk of G it fills
+    const int64_t row = m0 + r;
+    const float ls = p.ls[0];
+    const float k2 = ls * kLog2e;
+    const bool has_col = p.has_col != 0;
+    const float lx2 = (row < p.M ? p.lse_x[row] * kLog2e : 0.f) - (log2f(p.w_row) + 12.f);
+    const float w_diag_s = p.w_diag * kGScale;
+    const int64_t jd = row + p.diag_off;
+    float rd = 0.f;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int64_t blk_lo = (int64_t)(blockIdx.x >> 1) * 128 + p.diag_off;   // diagonal columns of the pair's rows
+    for (int st = 0; st < nsteps; ++st) {
+      const int buf = st & 1;
+      const uint32_t bph = (st >> 1) & 1;
+      const int64_t n0 = (int64_t)(s0 + st) * 256;
+      mbar_wait(sfull_bar(buf), bph);
+      mbar_wait(gempty_bar(buf), bph ^ 1);      // dX of step st-2 has finished reading this G buffer
+      tc_fence_after();
+      const bool special = (n0 + 256 > p.N) || (n0 < blk_lo + 128 && n0 + 256 > blk_lo);
+      const uint32_t g_row = g_base + (buf * 4 + kc) * kTile8K + r * 128;
+#pragma unroll 1
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t v[32];
+        uint32_t g[16];
+        tmem_ld32(lane_addr + buf * 128 + half * 64 + cc * 32, v);
+        tmem_ld_wait();
+        const int64_t col0 = n0 + cS + cc * 32;
+        const float* ly2 = has_col ? p.ly2 + col0 : nullptr;
+        if (special) {
+          if (has_col) bwd2_chunk<true, true>(v, g, k2, lx2, ly2, w_diag_s, col0, p.N, jd, rd);
+          else bwd2_chunk<true, false>(v, g, k2, lx2, ly2, w_diag_s, col0, p.N, jd, rd);
+        } else {
+          if (has_col) bwd2_chunk<false, true>(v, g, k2, lx2, ly2, w_diag_s, col0, p.N, jd, rd);
+          else bwd2_chunk<false, false>(v, g, k2, lx2, ly2, w_diag_s, col0, p.N, jd, rd);
+        }
+        // 32 f16 = four 16-byte pieces (cc*4 .. cc*4+3) of this row's 128-byte line, 128B-swizzled
+#pragma unroll
+        for (int pc = 0; pc < 4; ++pc) {
+          const uint32_t piece = (uint32_t)((cc * 4 + pc) ^ (r & 7));
+          st_shared_v4(g_row + piece * 16, g[4 * pc], g[4 * pc + 1], g[4 * pc + 2], g[4 * pc + 3]);
+        }
+      }
+      tc_fence_before();          // TMEM reads of S are complete
+      fence_proxy_async_smem();   // G visible to the tensor-core (async) proxy
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(gfull_bar(buf)); else mbar_arrive_cluster(gfull_bar(buf), 0);
+      }
+    }
+    // ---- dX accumulator -> global ----
+    mbar_wait(dxfull_bar, 0);
+    tc_fence_after();
+    const float alpha = (p.go ? p.go[0] : 1.f) * ls * p.inv_2n * (1.f / kGScale);
+    for (int h = 0; h < p.ndh; ++h) {
+#pragma unroll 1
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t v[32];
+        tmem_ld32(lane_addr + kDxCol + h * 128 + half * 64 + cc * 32, v);
+        tmem_ld_wait();
+        const int64_t d0 = (int64_t)h * 256 + (q >> 1) * 128 + half * 64 + cc * 32;
+        if (row < p.M && nsteps > 0 && d0 < p.D) {
+          if (p.nsplit > 1) {
+            float* dst = p.acc_ws + ((int64_t)blockIdx.y * p.M + row) * p.D + d0;
+            if (d0 + 32 <= p.D) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<uint4*>(dst + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (d0 + j < p.D) dst[j] = __uint_as_float(v[j]);
+            }
+          } else if (d0 + 32 <= p.D) {
+            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.dX) + row * p.lddx + d0);
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 o;
+              float f[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j + e]) * alpha;
+              o.x = kBF16 ? pack_bf16x2(f[0], f[1]) : pack_f16x2(f[0], f[1]);
+              o.y = kBF16 ? pack_bf16x2(f[2], f[3]) : pack_f16x2(f[2], f[3]);
+              o.z = kBF16 ? pack_bf16x2(f[4], f[5]) : pack_f16x2(f[4], f[5]);
+              o.w = kBF16 ? pack_bf16x2(f[6], f[7]) : pack_f16x2(f[6], f[7]);
+              dst[j >> 3] = o;
+            }
+          } else {
+            uint16_t* dst = reinterpret_cast<uint16_t*>(p.dX) + row * p.lddx + d0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (d0 + j < p.D) {
+                const uint32_t pk = kBF16 ? pack_bf16x2(__uint_as_float(v[j]) * alpha, 0.f)
+                                          : pack_f16x2(__uint_as_float(v[j]) * alpha, 0.f);
+                dst[j] = (uint16_t)(pk & 0xFFFFu);
+              }
+            }
+          }
+        }
+      }
+    }
+    // rowdot: four threads share a row (2 lane halves x 2 column halves); add in fixed order via shared memory
+    if (p.rowdot != nullptr) {
+      rd_scratch[((q >> 1) * 2 + half) * 64 + r] = rd;
+      named_bar_sync(1, kEpiThreads);
+      if ((q >> 1) == 0 && half == 0 && row < p.M) {
+        const float tot = ((rd_scratch[r] + rd_scratch[64 + r]) + (rd_scratch[128 + r] + rd_scratch[192 + r])) * (1.f / kGScale);
+        if (p.nsplit > 1) p.rd_ws[(int64_t)blockIdx.y * p.M + row] = tot;
+        else p.rowdot[row] = tot;
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_cg2(tmem_base, kTmemCols);
+  }
+}
+
+// lse_y -> log2 units with the column weight and the G scale folded in, +inf padded to a multiple of 256
+__global__ void prep_ly2_kernel(const float* __restrict__ lse_y, int64_t N, int64_t n_pad, float lw_col,
+                                float* __restrict__ ly2) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_pad) ly2[i] = i < N ? lse_y[i] * kLog2e - lw_col : INFINITY;
+}
+
+// bf16 -> f16 copy of Y (exact for 6.1e-5 <= |v| <= 65504; saturating above, f16-subnormal below)
+__global__ void bf16_to_f16_kernel(const __nv_bfloat16* __restrict__ src, int64_t rows, int64_t D, int64_t ld,
+                                   __half* __restrict__ dst) {
+  const int64_t n8 = rows * (D / 8);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / (D / 8), c = (i - r * (D / 8)) * 8;
+    const uint4 in = *reinterpret_cast<const uint4*>(src + r * ld + c);
+    const __nv_bfloat162* b = reinterpret_cast<const __nv_bfloat162*>(&in);
+    uint4 out;
+    __half2* h = reinterpret_cast<__half2*>(&out);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float2 f = __bfloat1622float2(b[e]);
+      f.x = fminf(fmaxf(f.x, -65504.f), 65504.f);
+      f.y = fminf(fmaxf(f.y, -65504.f), 65504.f);
+      h[e] = __floats2half2_rn(f.x, f.y);
+    }
+    *reinterpret_cast<uint4*>(dst + r * D + c) = out;
   }
 }
 
@@ -547,6 +975,27 @@ __global__ void acc_to_dx_kernel(const float* __restrict__ acc, int64_t M, int64
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// MCLIP_BWD_1CTA=1 forces the single-CTA backward kernel also for D <= 512 (development A/B switch).
+bool use_single_cta_bwd() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("MCLIP_BWD_1CTA");
+    cached = (e && e[0] == '1') ? 1 : 0;
+  }
+  return cached == 1;
+}
+
+// Driver-API calls (cuTensorMapEncodeTiled) need the primary context bound to the calling thread; autograd's
+// backward threads may not have touched the runtime yet.  cudaFree(0) binds it (no-op otherwise).
+int bind_context() {
+  static thread_local bool bound = false;
+  if (!bound) {
+    MCLIP_CUDA_OK(cudaFree(0));
+    bound = true;
+  }
+  return MCLIP_OK;
+}
 
 int get_encode_fn(EncodeTiledFn* out) {
   static EncodeTiledFn cached = nullptr;
@@ -567,7 +1016,9 @@ int get_encode_fn(EncodeTiledFn* out) {
 // [rows, D] row-major 16-bit matrix, box = [box_rows x 64 elements], 128-byte swizzle, zero fill.
 int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t D, int64_t ld, int dtype, uint32_t box_rows) {
   EncodeTiledFn enc;
-  int rc = get_encode_fn(&enc);
+  int rc = bind_context();
+  if (rc) return rc;
+  rc = get_encode_fn(&enc);
   if (rc) return rc;
   const cuuint64_t gdim[2] = {(cuuint64_t)D, (cuuint64_t)rows};
   const cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
@@ -647,6 +1098,45 @@ BwdPlan plan_bwd(int64_t M, int64_t N, int64_t D) {
   return b;
 }
 
+struct Bwd2Plan { int kch; int kpairs; int ndh; int steps_total; int nsplit; int steps_per_split; uint32_t smem; };
+
+Bwd2Plan plan_bwd2(int64_t M, int64_t N, int64_t D) {
+  Bwd2Plan b;
+  b.kch = (int)ceil_div(D, 64);
+  b.kpairs = (b.kch + 1) / 2;
+  b.ndh = (int)ceil_div(D, 256);
+  b.steps_total = (int)ceil_div(N, 256);
+  const int64_t pairs = ceil_div(M, 128);
+  int best = 1;
+  double best_cost = 1e30;
+  const int max_split = b.steps_total < 32 ? b.steps_total : 32;
+  for (int s = 1; s <= max_split; ++s) {
+    const int sps = (int)ceil_div(b.steps_total, s);
+    const int real = (int)ceil_div(b.steps_total, sps);
+    if (real != s) continue;
+    const double waves = (double)ceil_div(pairs * s, 74);   // 74 CTA pairs per wave
+    const double cost = waves * (sps + 2.0) + (s > 1 ? 0.02 * b.steps_total : 0.0);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
+  }
+  b.nsplit = best;
+  b.steps_per_split = (int)ceil_div(b.steps_total, best);
+  b.smem = kAlignSlack + 8 * kTile8K + 8 * kTile8K + kRing2 * kStage2 + 1536;
+  return b;
+}
+
+// workspace carve-up shared by the size query and the launcher
+struct BwdWs { size_t acc, rd, ly2, y16, total; };
+BwdWs bwd_ws_layout(int nsplit, int64_t M, int64_t N, int64_t D, int64_t n_pad, bool need_y16) {
+  BwdWs w;
+  size_t off = 0;
+  w.acc = off; off += nsplit > 1 ? align_up((size_t)nsplit * M * D * sizeof(float), 256) : 0;
+  w.rd = off;  off += nsplit > 1 ? align_up((size_t)nsplit * M * sizeof(float), 256) : 0;
+  w.ly2 = off; off += align_up((size_t)n_pad * sizeof(float), 256);
+  w.y16 = off; off += need_y16 ? align_up((size_t)N * D * 2, 256) : 0;
+  w.total = off;
+  return w;
+}
+
 template <typename K>
 int set_smem(K kernel, uint32_t bytes) {
   MCLIP_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -669,8 +1159,13 @@ size_t tc_row_lse_ws(int64_t M, int64_t N, int64_t D) {
 }
 
 size_t tc_block_grad_ws(int64_t M, int64_t N, int64_t D) {
+  if (D <= 512) {
+    const Bwd2Plan b = plan_bwd2(M, N, D);
+    // dtype is not known here: always reserve room for the f16 copy of Y
+    return bwd_ws_layout(b.nsplit, M, N, D, (int64_t)b.steps_total * 256, true).total;
+  }
   const BwdPlan b = plan_bwd(M, N, D);
-  return b.nsplit > 1 ? align_up((size_t)M * D * sizeof(float), 256) : 0;
+  return b.nsplit > 1 ? align_up((size_t)b.nsplit * M * (D + 1) * sizeof(float), 256) : 0;
 }
 
 int tc_row_lse(const RowLseArgs& a) {
@@ -704,9 +1199,80 @@ int tc_row_lse(const RowLseArgs& a) {
   return launch_lse_merge(p.part_m2, p.part_s, f.nsplit, a.M, a.lse, a.stream);
 }
 
+// CTA-pair backward (D <= 512)
+int tc_block_grad2(const BlockGradArgs& a) {
+  const Bwd2Plan b = plan_bwd2(a.M, a.N, a.D);
+  const bool bf = a.dtype == MCLIP_DTYPE_BF16;
+  const int64_t n_pad = (int64_t)b.steps_total * 256;
+  const BwdWs w = bwd_ws_layout(b.nsplit, a.M, a.N, a.D, n_pad, bf);
+  if (w.total > a.ws_bytes) { set_error("block_grad(tcgen05): workspace %zu < %zu", a.ws_bytes, w.total); return MCLIP_ERR_WORKSPACE; }
+  uint8_t* ws = reinterpret_cast<uint8_t*>(a.ws);
+  float* ly2 = reinterpret_cast<float*>(ws + w.ly2);
+  const bool has_col = a.w_col != 0.f;
+  if (has_col) {
+    prep_ly2_kernel<<<(unsigned)ceil_div(n_pad, 256), 256, 0, a.stream>>>(a.lse_y, a.N, n_pad, log2f(a.w_col) + 12.f, ly2);
+    count_launch();
+    MCLIP_CUDA_OK(cudaGetLastError());
+  }
+  const void* y16 = a.Y;
+  int64_t ld16 = a.ldy;
+  if (bf) {
+    __half* dst = reinterpret_cast<__half*>(ws + w.y16);
+    const int64_t n8 = a.N * (a.D / 8);
+    const unsigned blocks = (unsigned)(ceil_div(n8, 256) < 148 * 8 ? ceil_div(n8, 256) : 148 * 8);
+    bf16_to_f16_kernel<<<blocks, 256, 0, a.stream>>>(reinterpret_cast<const __nv_bfloat16*>(a.Y), a.N, a.D, a.ldy, dst);
+    count_launch();
+    MCLIP_CUDA_OK(cudaGetLastError());
+    y16 = dst;
+    ld16 = a.D;
+  }
+  CUtensorMap tmX, tmY, tmY16;
+  int rc = make_tmap(&tmX, a.X, a.M, a.D, a.ldx, a.dtype, 64);
+  if (rc) return rc;
+  rc = make_tmap(&tmY, a.Y, a.N, a.D, a.ldy, a.dtype, 128);
+  if (rc) return rc;
+  rc = make_tmap(&tmY16, y16, a.N, a.D, ld16, MCLIP_DTYPE_F16, 128);
+  if (rc) return rc;
+  Bwd2Params p;
+  p.M = a.M; p.N = a.N; p.D = a.D; p.kpairs = b.kpairs; p.ndh = b.ndh; p.steps_total = b.steps_total;
+  p.steps_per_split = b.steps_per_split; p.nsplit = b.nsplit; p.diag_off = a.diag_off; p.ls = a.logit_scale;
+  p.go = a.grad_out; p.lse_x = a.lse_x; p.ly2 = has_col ? ly2 : nullptr; p.w_row = a.w_row; p.w_diag = a.w_diag;
+  p.inv_2n = a.inv_2n; p.has_col = has_col ? 1 : 0; p.dX = a.dX; p.lddx = a.lddx;
+  p.acc_ws = reinterpret_cast<float*>(ws + w.acc); p.rd_ws = reinterpret_cast<float*>(ws + w.rd); p.rowdot = a.rowdot;
+  dim3 grid((unsigned)(2 * ceil_div(a.M, 128)), (unsigned)b.nsplit);
+  if (bf) {
+    rc = set_smem(tc_block_grad2_kernel<true>, b.smem);
+    if (rc) return rc;
+    tc_block_grad2_kernel<true><<<grid, kThreads, b.smem, a.stream>>>(tmX, tmY, tmY16, p);
+  } else {
+    rc = set_smem(tc_block_grad2_kernel<false>, b.smem);
+    if (rc) return rc;
+    tc_block_grad2_kernel<false><<<grid, kThreads, b.smem, a.stream>>>(tmX, tmY, tmY16, p);
+  }
+  count_launch();
+  MCLIP_CUDA_OK(cudaGetLastError());
+  if (b.nsplit > 1) {
+    const int64_t n = a.M * a.D;
+    const unsigned blocks = (unsigned)(ceil_div(n, 1024) < 148 * 8 ? ceil_div(n, 1024) : 148 * 8);
+    const float scale = a.inv_2n * (1.f / kGScale);
+    if (bf)
+      acc_to_dx_kernel<__nv_bfloat16><<<blocks, 256, 0, a.stream>>>(p.acc_ws, p.rd_ws, b.nsplit, a.M, a.D, a.logit_scale,
+                                                                   a.grad_out, scale,
+                                                                   reinterpret_cast<__nv_bfloat16*>(a.dX), a.lddx, a.rowdot);
+    else
+      acc_to_dx_kernel<__half><<<blocks, 256, 0, a.stream>>>(p.acc_ws, p.rd_ws, b.nsplit, a.M, a.D, a.logit_scale,
+                                                            a.grad_out, scale, reinterpret_cast<__half*>(a.dX), a.lddx,
+                                                            a.rowdot);
+    count_launch();
+    MCLIP_CUDA_OK(cudaGetLastError());
+  }
+  return MCLIP_OK;
+}
+
 int tc_block_grad(const BlockGradArgs& a) {
   if (((uintptr_t)a.X | (uintptr_t)a.Y | (uintptr_t)a.dX) & 15) { set_error("block_grad(tcgen05): X/Y/dX must be 16-byte aligned"); return MCLIP_ERR_INVALID; }
   if (!(a.w_row > 0.f) || a.w_col < 0.f) { set_error("block_grad(tcgen05): needs w_row > 0 and w_col >= 0"); return MCLIP_ERR_INVALID; }
+  if (a.D <= 512 && !use_single_cta_bwd()) return tc_block_grad2(a);
   const BwdPlan b = plan_bwd(a.M, a.N, a.D);
   if (b.stages < 2) { set_error("block_grad(tcgen05): not enough shared memory for D=%lld", (long long)a.D); return MCLIP_ERR_UNSUPPORTED; }
   CUtensorMap tmX, tmY;
@@ -720,32 +1286,37 @@ int tc_block_grad(const BlockGradArgs& a) {
   p.go = a.grad_out; p.lse_x = a.lse_x; p.lse_y = a.lse_y; p.w_row = a.w_row; p.w_col = a.w_col;
   p.w_diag = a.w_diag; p.inv_2n = a.inv_2n; p.dX = a.dX; p.lddx = a.lddx;
   p.acc_ws = reinterpret_cast<float*>(a.ws); p.rowdot = a.rowdot;
-  if (b.nsplit > 1) MCLIP_CUDA_OK(cudaMemsetAsync(a.ws, 0, sizeof(float) * a.M * a.D, a.stream));
-  if (a.rowdot) MCLIP_CUDA_OK(cudaMemsetAsync(a.rowdot, 0, sizeof(float) * a.M, a.stream));
+  p.rd_ws = p.acc_ws + (size_t)b.nsplit * a.M * a.D;
   dim3 grid((unsigned)ceil_div(a.M, 128), (unsigned)b.dchunks, (unsigned)b.nsplit);
   const bool bf = a.dtype == MCLIP_DTYPE_BF16;
-#define MCLIP_LAUNCH_BWD(BF, XR)                                                              \
+  const bool g_bf16 = bf;   // kind::f16 needs A and B in the same format: G follows the inputs on this path
+#define MCLIP_LAUNCH_BWD(BF, XR, GF)                                                          \
   do {                                                                                        \
-    rc = set_smem(tc_block_grad_kernel<BF, XR>, b.smem);                                      \
+    rc = set_smem(tc_block_grad_kernel<BF, XR, GF>, b.smem);                                  \
     if (rc) return rc;                                                                        \
-    tc_block_grad_kernel<BF, XR><<<grid, kThreads, b.smem, a.stream>>>(tmX, tmY, p);          \
+    tc_block_grad_kernel<BF, XR, GF><<<grid, kThreads, b.smem, a.stream>>>(tmX, tmY, p);      \
   } while (0)
-  if (bf && b.xres) MCLIP_LAUNCH_BWD(true, true);
-  else if (bf) MCLIP_LAUNCH_BWD(true, false);
-  else if (b.xres) MCLIP_LAUNCH_BWD(false, true);
-  else MCLIP_LAUNCH_BWD(false, false);
+  if (bf && b.xres && !g_bf16) MCLIP_LAUNCH_BWD(true, true, true);
+  else if (bf && b.xres) MCLIP_LAUNCH_BWD(true, true, false);
+  else if (bf && !g_bf16) MCLIP_LAUNCH_BWD(true, false, true);
+  else if (bf) MCLIP_LAUNCH_BWD(true, false, false);
+  else if (b.xres) MCLIP_LAUNCH_BWD(false, true, true);
+  else MCLIP_LAUNCH_BWD(false, false, true);
 #undef MCLIP_LAUNCH_BWD
   count_launch();
   MCLIP_CUDA_OK(cudaGetLastError());
   if (b.nsplit > 1) {
     const int64_t n = a.M * a.D;
-    const unsigned blocks = (unsigned)(ceil_div(n, 256) < 148 * 8 ? ceil_div(n, 256) : 148 * 8);
+    const unsigned blocks = (unsigned)(ceil_div(n, 1024) < 148 * 8 ? ceil_div(n, 1024) : 148 * 8);
+    const float scale = a.inv_2n * (g_bf16 ? 1.f : 1.f / 4096.f);
     if (bf)
-      acc_to_dx_kernel<__nv_bfloat16><<<blocks, 256, 0, a.stream>>>(p.acc_ws, a.M, a.D, a.logit_scale, a.grad_out,
-                                                                   a.inv_2n, reinterpret_cast<__nv_bfloat16*>(a.dX), a.lddx);
+      acc_to_dx_kernel<__nv_bfloat16><<<blocks, 256, 0, a.stream>>>(p.acc_ws, p.rd_ws, b.nsplit, a.M, a.D, a.logit_scale,
+                                                                   a.grad_out, scale,
+                                                                   reinterpret_cast<__nv_bfloat16*>(a.dX), a.lddx, a.rowdot);
     else
-      acc_to_dx_kernel<__half><<<blocks, 256, 0, a.stream>>>(p.acc_ws, a.M, a.D, a.logit_scale, a.grad_out, a.inv_2n,
-                                                            reinterpret_cast<__half*>(a.dX), a.lddx);
+      acc_to_dx_kernel<__half><<<blocks, 256, 0, a.stream>>>(p.acc_ws, p.rd_ws, b.nsplit, a.M, a.D, a.logit_scale,
+                                                            a.grad_out, scale, reinterpret_cast<__half*>(a.dX), a.lddx,
+                                                            a.rowdot);
     count_launch();
     MCLIP_CUDA_OK(cudaGetLastError());
   }

@@ -53,6 +53,9 @@ def run_case(kind, M, N, D, ls, diag_off, dtype, oracle):
         rel = float((af - bf).norm() / bf.norm().clamp_min(1e-30))
         print(f"bwd {M}x{N}x{D} ls={ls}: tc-vs-simt dX rel={rel:.3e} |simt|={float(bf.norm()):.3e} rowdot max|d|={float((ra - rb).abs().max()):.3e}"
               f" nan={int(torch.isnan(af).sum())}")
+        if oracle:
+            ref, _ = O.block_grad(x.float(), y.float(), ls, lx.cpu(), ly.cpu(), diag_off, 1.0, 1.0, 2.0, 2.0 * ls * 0.5 / M)
+            print(f"  vs fp64 oracle: tc rel={O.rel_err(a.cpu(), ref):.3e}  simt rel={O.rel_err(b.cpu(), ref):.3e}  (kernel: {'1-CTA' if os.environ.get('MCLIP_BWD_1CTA') == '1' else 'CTA pair'})")
         if rel > 5e-3 or torch.isnan(af).any():
             err = (af - bf).abs()
             rows = err.max(dim=1).values
@@ -96,7 +99,8 @@ CASES = [
     ("fwd", 129, 300, 512, 100.0, 64), ("fwd", 512, 4096, 512, 30.0, 1024), ("fwd", 300, 1000, 768, 30.0, 17),
     ("bwd", 128, 128, 64, 10.0, 0), ("bwd", 128, 128, 256, 10.0, 0), ("bwd", 128, 128, 512, 14.2857, 0),
     ("bwd", 128, 256, 512, 14.2857, 0), ("bwd", 129, 300, 512, 30.0, 64), ("bwd", 512, 4096, 512, 30.0, 1024),
-    ("bwd", 300, 1000, 768, 30.0, 17),
+    ("bwd", 300, 1000, 768, 30.0, 17), ("bwd", 64, 64, 64, 14.2857, 0), ("bwd", 1000, 3000, 384, 14.2857, 100), ("bwd", 2048, 2048, 512, 14.2857, 0),
+    ("bwd_1cta", 128, 128, 512, 14.2857, 0), ("bwd_1cta", 512, 4096, 512, 30.0, 1024),
 ]
 TIMES = [("fwd", 8192, 8192, 512), ("bwd", 8192, 8192, 512), ("fwd", 32768, 32768, 512), ("bwd", 32768, 32768, 512)]
 
@@ -107,7 +111,7 @@ if __name__ == "__main__":
     args = ap.parse_args()
     if args.one:
         a = args.one
-        if a[0] == "time":
+        if a[0] in ("time", "time_1cta"):
             time_case(a[1], int(a[2]), int(a[3]), int(a[4]), "bf16", 5)
         else:
             run_case(a[0], int(a[1]), int(a[2]), int(a[3]), float(a[4]), int(a[5]), "bf16", int(a[1]) * int(a[2]) <= 1 << 22)
@@ -115,10 +119,15 @@ if __name__ == "__main__":
     jobs = [[c[0]] + [str(v) for v in c[1:]] for c in CASES]
     if not args.no_time:
         jobs += [["time"] + [str(v) for v in t] for t in TIMES]
+        jobs += [["time_1cta", "bwd", "32768", "32768", "512"]]
     for j in jobs:
         t0 = time.time()
+        env = dict(os.environ)
+        if j[0].endswith("_1cta"):
+            j = [j[0][:-5]] + j[1:]
+            env["MCLIP_BWD_1CTA"] = "1"
         try:
-            r = subprocess.run([sys.executable, __file__, "--one"] + j, capture_output=True, text=True, timeout=150)
+            r = subprocess.run([sys.executable, __file__, "--one"] + j, capture_output=True, text=True, timeout=150, env=env)
             out = (r.stdout + ("\n[stderr] " + r.stderr[-1500:] if r.returncode != 0 else "")).strip()
             print(out, f"[rc={r.returncode} {time.time() - t0:.1f}s]", flush=True)
         except subprocess.TimeoutExpired:
