@@ -616,11 +616,12 @@ struct Bwd2Params {
   float* acc_ws;
   float* rd_ws;
   float* rowdot;
+  int dbg;              // development switches (MCLIP_DBG): 1 = epilogue without math, 2 = no S MMAs, 4 = no dX MMAs
 };
 
 constexpr uint32_t kTile8K = 64 * 64 * 2;     // [64 rows x 64 k]
 constexpr uint32_t kStage2 = 2 * kChunkBytes; // ring stage: two [128 x 64] tiles
-constexpr int kRing2 = 3;
+constexpr int kRing2 = 4;
 constexpr float kGScale = 4096.f;             // G is stored as G * 2^12 in f16
 
 template <bool kMasked, bool kCol>
@@ -655,16 +656,19 @@ __device__ __forceinline__ void bwd2_chunk(const uint32_t (&v)[32], uint32_t (&g
   }
 }
 
-template <bool kBF16>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+// kPairs = 2: a cluster of four CTAs = two pairs working on adjacent 128-row blocks.  Both pairs need the same Y
+// tiles, so each CTA issues half of the TMA boxes and multicasts them to its counterpart in the other pair:
+// L2 -> SM traffic per flop halves (the pair kernel alone streams 62 B/clk/SM, at the measured L2 limit).
+template <bool kBF16, int kPairs>
+__global__ void __launch_bounds__(kThreads, 1)
 tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
                       const __grid_constant__ CUtensorMap tmY16, const Bwd2Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = align1024(smem_u32(smem_raw));
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t x_base = smem_base;                              // [8][64 rows][64 k]   64 KB
-  const uint32_t g_base = x_base + 8 * kTile8K;                   // [2][4][64 rows][64 y] 64 KB
-  const uint32_t ring_base = g_base + 2 * 4 * kTile8K;            // [kRing2][2][128][64]  96 KB
+  const uint32_t g_base = x_base + 8 * kTile8K;                   // [4][64 rows][64 y]    32 KB (single buffer)
+  const uint32_t ring_base = g_base + 4 * kTile8K;                // [kRing2][2][128][64]  128 KB
   const uint32_t misc_base = ring_base + kRing2 * kStage2;
   uint8_t* misc_gen = smem_gen + (misc_base - smem_base);
   const uint32_t bar_base = misc_base;
@@ -672,17 +676,23 @@ tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   auto empty_bar = [&](int s) { return bar_base + 8u * (4 + s); };      // per CTA, MMA commit multicast
   const uint32_t xfull_bar = bar_base + 8u * 8;                          // leader
   auto sfull_bar = [&](int b) { return bar_base + 8u * (9 + b); };      // per CTA, multicast
-  auto gfull_bar = [&](int b) { return bar_base + 8u * (11 + b); };     // leader: 16 epilogue warps
-  auto gempty_bar = [&](int b) { return bar_base + 8u * (13 + b); };    // per CTA, multicast
+  const uint32_t gfull_bar = bar_base + 8u * 11;                         // leader: 16 epilogue warps
+  const uint32_t gempty_bar = bar_base + 8u * 13;                        // per CTA, multicast
   const uint32_t dxfull_bar = bar_base + 8u * 15;                        // per CTA, multicast
   const uint32_t tmem_slot = bar_base + 8u * 16;
   uint32_t* tmem_slot_gen = reinterpret_cast<uint32_t*>(misc_gen + 8u * 16);
   float* rd_scratch = reinterpret_cast<float*>(misc_gen + 256);          // [4][64]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
+  const uint32_t crank = cluster_ctarank();          // 0 .. 2*kPairs-1
+  const uint32_t rank = crank & 1;                   // role inside the pair
+  const uint32_t pr = crank >> 1;                    // pair inside the cluster
+  const uint32_t leader_rank = crank & ~1u;
   const bool leader = rank == 0;
-  const int64_t m0 = (int64_t)(blockIdx.x >> 1) * 128 + 64 * rank;   // this CTA's 64 rows
+  constexpr uint16_t kAllMask = (uint16_t)((1u << (2 * kPairs)) - 1);
+  const uint16_t pair_mask = (uint16_t)(3u << (2 * pr));
+  const int64_t pair_row0 = (int64_t)(blockIdx.x / (2 * kPairs)) * (128 * kPairs) + 128 * pr;
+  const int64_t m0 = pair_row0 + 64 * rank;          // this CTA's 64 rows
   const int s0 = blockIdx.y * p.steps_per_split;
   const int s1 = min(p.steps_total, s0 + p.steps_per_split);
   const int nsteps = s1 - s0;
@@ -693,13 +703,11 @@ tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmY);
     tma_prefetch_desc(&tmY16);
-    for (int s = 0; s < kRing2; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < kRing2; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), kPairs); }
     mbar_init(xfull_bar, 2);
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(sfull_bar(b), 1);
-      mbar_init(gfull_bar(b), 2 * (kEpiThreads / 32));
-      mbar_init(gempty_bar(b), 1);
-    }
+    for (int b = 0; b < 2; ++b) mbar_init(sfull_bar(b), 1);
+    mbar_init(gfull_bar, 2 * (kEpiThreads / 32));
+    mbar_init(gempty_bar, 1);
     mbar_init(dxfull_bar, 1);
     fence_barrier_init();
   } else if (warp == 2) {
@@ -714,24 +722,31 @@ tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   if (warp == 0) {
     if (lane == 0) {
       // ---------------- TMA producer (both CTAs; bytes are credited to the leader's barriers) ----------------
-      if (leader) mbar_expect_tx(xfull_bar, 2 * 8 * kTile8K); else mbar_arrive_cluster(xfull_bar, 0);
+      if (leader) mbar_expect_tx(xfull_bar, 2 * 8 * kTile8K); else mbar_arrive_cluster(xfull_bar, leader_rank);
       for (int c = 0; c < 8; ++c) tma_load_2d_cg2(x_base + c * kTile8K, &tmX, c * 64, (int32_t)m0, xfull_bar);
       uint32_t it = 0;
       auto stage_begin = [&]() -> uint32_t {
         const int s = it % kRing2;
         const uint32_t ph = (it / kRing2) & 1;
         mbar_wait(empty_bar(s), ph ^ 1);
-        if (leader) mbar_expect_tx(full_bar(s), 2 * kStage2); else mbar_arrive_cluster(full_bar(s), 0);
+        if (leader) mbar_expect_tx(full_bar(s), 2 * kStage2); else mbar_arrive_cluster(full_bar(s), leader_rank);
         ++it;
         return (uint32_t)s;
+      };
+      // one ring stage = two boxes.  kPairs == 1: this CTA loads both.  kPairs == 2: it loads box `pr` and multicasts
+      // it to the CTA with the same role in the other pair (which loads and multicasts the other box).
+      const uint16_t mc_mask = (uint16_t)((1u << rank) | (1u << (rank + 2)));
+      auto load_box = [&](uint32_t dst, const CUtensorMap* tm, int e, int32_t c_inner, int32_t c_outer, uint32_t bar) {
+        if (kPairs == 1) tma_load_2d_cg2(dst + e * kChunkBytes, tm, c_inner, c_outer, bar);
+        else if ((uint32_t)e == pr) tma_load_2d_cg2_mc(dst + e * kChunkBytes, tm, c_inner, c_outer, bar, mc_mask);
       };
       auto load_s = [&](int st) {   // Y tiles of step st as the N operand of S: this CTA's 128 rows, all of D
         const int32_t y0 = (s0 + st) * 256 + 128 * (int32_t)rank;
         for (int i = 0; i < p.kpairs; ++i) {
           const uint32_t s = stage_begin();
           const uint32_t dst = ring_base + s * kStage2;
-          tma_load_2d_cg2(dst, &tmY, (2 * i) * 64, y0, full_bar(s));
-          tma_load_2d_cg2(dst + kChunkBytes, &tmY, (2 * i + 1) * 64, y0, full_bar(s));
+          load_box(dst, &tmY, 0, (2 * i) * 64, y0, full_bar(s));
+          load_box(dst, &tmY, 1, (2 * i + 1) * 64, y0, full_bar(s));
         }
       };
       auto load_dx = [&](int st) {  // Y16 tiles of step st as the [K = y][N = d] operand of dX: all 256 rows, this CTA's d
@@ -741,8 +756,8 @@ tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
             const uint32_t s = stage_begin();
             const uint32_t dst = ring_base + s * kStage2;
             const int32_t dcol = (4 * h + 2 * (int32_t)rank) * 64;
-            tma_load_2d_cg2(dst, &tmY16, dcol, y0, full_bar(s));
-            tma_load_2d_cg2(dst + kChunkBytes, &tmY16, dcol + 64, y0, full_bar(s));
+            load_box(dst, &tmY16, 0, dcol, y0, full_bar(s));
+            load_box(dst, &tmY16, 1, dcol + 64, y0, full_bar(s));
           }
         }
       };
@@ -781,17 +796,15 @@ tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
             for (int k = 0; k < 4; ++k) {
               const uint64_t ad = make_smem_desc_sw128(x_base + (2 * i + e) * kTile8K + k * 32, 0, 1024);
               const uint64_t bd = make_smem_desc_sw128(b_addr + e * kChunkBytes + k * 32, 0, 1024);
-              mma_ss_cg2(d_tmem, ad, bd, idesc_s, (i | e | k) != 0);
+              if (!(p.dbg & 2)) mma_ss_cg2(d_tmem, ad, bd, idesc_s, (i | e | k) != 0);
             }
           }
-          mma_commit_cg2(empty_bar(s), 3);
+          mma_commit_cg2(empty_bar(s), kAllMask);
         }
-        mma_commit_cg2(sfull_bar(buf), 3);
+        mma_commit_cg2(sfull_bar(buf), pair_mask);
       };
       auto issue_dx = [&](int st) {
-        const int buf = st & 1;
-        const uint32_t bph = (st >> 1) & 1;
-        mbar_wait(gfull_bar(buf), bph);
+        mbar_wait(gfull_bar, st & 1);
         tc_fence_after();
         for (int yh = 0; yh < 2; ++yh) {
           for (int h = 0; h < p.ndh; ++h) {
@@ -800,21 +813,21 @@ tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk) {
               // A = G[64 rows x 16 y] of K-chunk (2*yh + kk/4); B = Y16[16 y][128 d per CTA], MN-major
-              const uint64_t ad = make_smem_desc_sw128(g_base + (buf * 4 + 2 * yh + (kk >> 2)) * kTile8K + (kk & 3) * 32, 0, 1024);
+              const uint64_t ad = make_smem_desc_sw128(g_base + (2 * yh + (kk >> 2)) * kTile8K + (kk & 3) * 32, 0, 1024);
               const uint64_t bd = make_smem_desc_sw128(b_addr + kk * 2048, kChunkBytes, 1024);
-              mma_ss_cg2(tmem_base + kDxCol + h * 128, ad, bd, idesc_dx, (st | yh | kk) != 0);
+              if (!(p.dbg & 4)) mma_ss_cg2(tmem_base + kDxCol + h * 128, ad, bd, idesc_dx, (st | yh | kk) != 0);
             }
-            mma_commit_cg2(empty_bar(s), 3);
+            mma_commit_cg2(empty_bar(s), kAllMask);
           }
         }
-        mma_commit_cg2(gempty_bar(buf), 3);
+        mma_commit_cg2(gempty_bar, pair_mask);
       };
       if (nsteps > 0) issue_s(0);
       for (int st = 0; st < nsteps; ++st) {
         if (st + 1 < nsteps) issue_s(st + 1);
         issue_dx(st);
       }
-      mma_commit_cg2(dxfull_bar, 3);
+      mma_commit_cg2(dxfull_bar, pair_mask);
     }
   } else if (warp >= kEpiWarp0) {
     // ---------------- epilogue: S -> G (f16 * 2^12) into shared memory; finally dX out ----------------
@@ -833,43 +846,51 @@ tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     const int64_t jd = row + p.diag_off;
     float rd = 0.f;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    const int64_t blk_lo = (int64_t)(blockIdx.x >> 1) * 128 + p.diag_off;   // diagonal columns of the pair's rows
+    const int64_t blk_lo = pair_row0 + p.diag_off;   // diagonal columns of the pair's rows
     for (int st = 0; st < nsteps; ++st) {
       const int buf = st & 1;
       const uint32_t bph = (st >> 1) & 1;
       const int64_t n0 = (int64_t)(s0 + st) * 256;
       mbar_wait(sfull_bar(buf), bph);
-      mbar_wait(gempty_bar(buf), bph ^ 1);      // dX of step st-2 has finished reading this G buffer
       tc_fence_after();
       const bool special = (n0 + 256 > p.N) || (n0 < blk_lo + 128 && n0 + 256 > blk_lo);
-      const uint32_t g_row = g_base + (buf * 4 + kc) * kTile8K + r * 128;
-#pragma unroll 1
+      const uint32_t g_row = g_base + kc * kTile8K + r * 128;
+      uint32_t g[2][16];
+#pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
         uint32_t v[32];
-        uint32_t g[16];
         tmem_ld32(lane_addr + buf * 128 + half * 64 + cc * 32, v);
         tmem_ld_wait();
         const int64_t col0 = n0 + cS + cc * 32;
         const float* ly2 = has_col ? p.ly2 + col0 : nullptr;
-        if (special) {
-          if (has_col) bwd2_chunk<true, true>(v, g, k2, lx2, ly2, w_diag_s, col0, p.N, jd, rd);
-          else bwd2_chunk<true, false>(v, g, k2, lx2, ly2, w_diag_s, col0, p.N, jd, rd);
+        if (p.dbg & 1) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) g[cc][j] = v[2 * j] & 0x3c003c00u;
+        } else if (special) {
+          if (has_col) bwd2_chunk<true, true>(v, g[cc], k2, lx2, ly2, w_diag_s, col0, p.N, jd, rd);
+          else bwd2_chunk<true, false>(v, g[cc], k2, lx2, ly2, w_diag_s, col0, p.N, jd, rd);
         } else {
-          if (has_col) bwd2_chunk<false, true>(v, g, k2, lx2, ly2, w_diag_s, col0, p.N, jd, rd);
-          else bwd2_chunk<false, false>(v, g, k2, lx2, ly2, w_diag_s, col0, p.N, jd, rd);
+          if (has_col) bwd2_chunk<false, true>(v, g[cc], k2, lx2, ly2, w_diag_s, col0, p.N, jd, rd);
+          else bwd2_chunk<false, false>(v, g[cc], k2, lx2, ly2, w_diag_s, col0, p.N, jd, rd);
         }
+      }
+      tc_fence_before();          // TMEM reads of S are complete
+      // G is single-buffered: the dX MMAs of the previous step must have finished reading it.  The values are
+      // already in registers, so this wait overlaps with the S MMAs of the next step on the tensor pipe.
+      mbar_wait(gempty_bar, (st & 1) ^ 1);
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
         // 32 f16 = four 16-byte pieces (cc*4 .. cc*4+3) of this row's 128-byte line, 128B-swizzled
 #pragma unroll
         for (int pc = 0; pc < 4; ++pc) {
           const uint32_t piece = (uint32_t)((cc * 4 + pc) ^ (r & 7));
-          st_shared_v4(g_row + piece * 16, g[4 * pc], g[4 * pc + 1], g[4 * pc + 2], g[4 * pc + 3]);
+          st_shared_v4(g_row + piece * 16, g[cc][4 * pc], g[cc][4 * pc + 1], g[cc][4 * pc + 2], g[cc][4 * pc + 3]);
         }
       }
-      tc_fence_before();          // TMEM reads of S are complete
       fence_proxy_async_smem();   // G visible to the tensor-core (async) proxy
       __syncwarp();
       if (lane == 0) {
-        if (leader) mbar_arrive(gfull_bar(buf)); else mbar_arrive_cluster(gfull_bar(buf), 0);
+        if (leader) mbar_arrive(gfull_bar); else mbar_arrive_cluster(gfull_bar, leader_rank);
       }
     }
     // ---- dX accumulator -> global ----
@@ -1098,15 +1119,27 @@ BwdPlan plan_bwd(int64_t M, int64_t N, int64_t D) {
   return b;
 }
 
-struct Bwd2Plan { int kch; int kpairs; int ndh; int steps_total; int nsplit; int steps_per_split; uint32_t smem; };
+struct Bwd2Plan { int kch; int kpairs; int ndh; int steps_total; int nsplit; int steps_per_split; uint32_t smem; int cpairs; };
+
+// MCLIP_BWD_PAIRS=1 selects clusters of one CTA pair (no multicast); default 2 pairs per cluster.
+int bwd_cluster_pairs() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("MCLIP_BWD_PAIRS");
+    cached = (e && e[0] == '1') ? 1 : 2;
+  }
+  return cached;
+}
 
 Bwd2Plan plan_bwd2(int64_t M, int64_t N, int64_t D) {
   Bwd2Plan b;
+  b.cpairs = (M > 128) ? bwd_cluster_pairs() : 1;
   b.kch = (int)ceil_div(D, 64);
   b.kpairs = (b.kch + 1) / 2;
   b.ndh = (int)ceil_div(D, 256);
   b.steps_total = (int)ceil_div(N, 256);
-  const int64_t pairs = ceil_div(M, 128);
+  const int64_t pairs = ceil_div(M, 128 * b.cpairs);       // clusters
+  const int per_wave = b.cpairs == 1 ? 74 : 33;            // clusters resident at once (4-CTA clusters strand 16 SMs)
   int best = 1;
   double best_cost = 1e30;
   const int max_split = b.steps_total < 32 ? b.steps_total : 32;
@@ -1114,13 +1147,13 @@ Bwd2Plan plan_bwd2(int64_t M, int64_t N, int64_t D) {
     const int sps = (int)ceil_div(b.steps_total, s);
     const int real = (int)ceil_div(b.steps_total, sps);
     if (real != s) continue;
-    const double waves = (double)ceil_div(pairs * s, 74);   // 74 CTA pairs per wave
+    const double waves = (double)ceil_div(pairs * s, per_wave);
     const double cost = waves * (sps + 2.0) + (s > 1 ? 0.02 * b.steps_total : 0.0);
     if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
   }
   b.nsplit = best;
   b.steps_per_split = (int)ceil_div(b.steps_total, best);
-  b.smem = kAlignSlack + 8 * kTile8K + 8 * kTile8K + kRing2 * kStage2 + 1536;
+  b.smem = kAlignSlack + 8 * kTile8K + 4 * kTile8K + kRing2 * kStage2 + 1536;
   return b;
 }
 
@@ -1239,16 +1272,33 @@ int tc_block_grad2(const BlockGradArgs& a) {
   p.go = a.grad_out; p.lse_x = a.lse_x; p.ly2 = has_col ? ly2 : nullptr; p.w_row = a.w_row; p.w_diag = a.w_diag;
   p.inv_2n = a.inv_2n; p.has_col = has_col ? 1 : 0; p.dX = a.dX; p.lddx = a.lddx;
   p.acc_ws = reinterpret_cast<float*>(ws + w.acc); p.rd_ws = reinterpret_cast<float*>(ws + w.rd); p.rowdot = a.rowdot;
-  dim3 grid((unsigned)(2 * ceil_div(a.M, 128)), (unsigned)b.nsplit);
-  if (bf) {
-    rc = set_smem(tc_block_grad2_kernel<true>, b.smem);
-    if (rc) return rc;
-    tc_block_grad2_kernel<true><<<grid, kThreads, b.smem, a.stream>>>(tmX, tmY, tmY16, p);
-  } else {
-    rc = set_smem(tc_block_grad2_kernel<false>, b.smem);
-    if (rc) return rc;
-    tc_block_grad2_kernel<false><<<grid, kThreads, b.smem, a.stream>>>(tmX, tmY, tmY16, p);
+  {
+    const char* e = getenv("MCLIP_DBG");
+    p.dbg = e ? atoi(e) : 0;
   }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * b.cpairs * ceil_div(a.M, 128 * b.cpairs)), (unsigned)b.nsplit);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = b.smem;
+  cfg.stream = a.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2 * b.cpairs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+#define MCLIP_LAUNCH_BWD2(BF, PAIRS)                                                        \
+  do {                                                                                      \
+    rc = set_smem(tc_block_grad2_kernel<BF, PAIRS>, b.smem);                                \
+    if (rc) return rc;                                                                      \
+    MCLIP_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_block_grad2_kernel<BF, PAIRS>, tmX, tmY, tmY16, p)); \
+  } while (0)
+  if (bf && b.cpairs == 2) MCLIP_LAUNCH_BWD2(true, 2);
+  else if (bf) MCLIP_LAUNCH_BWD2(true, 1);
+  else if (b.cpairs == 2) MCLIP_LAUNCH_BWD2(false, 2);
+  else MCLIP_LAUNCH_BWD2(false, 1);
+#undef MCLIP_LAUNCH_BWD2
   count_launch();
   MCLIP_CUDA_OK(cudaGetLastError());
   if (b.nsplit > 1) {

@@ -170,7 +170,7 @@ def test_clip_loss_against_reference_golden(k):
     B = case["B"]
     floor = 4 * 1.2e-7 * max(1.0, case["ls"]) * case["go"] * case["ls"] / (2 * B) * B ** 0.5
     if case["bf16"]:
-        floor *= 50   # G is rounded to bf16 before the MMA: absolute floor ~2^-9 of |G| <= 2
+        floor *= 2    # same fp32 exponent arithmetic as the FFMA path, plus ex2.approx (2 ulp)
     for key, g in (("di", img.grad), ("dt", txt.grad)):
         g = g.detach().cpu().double()
         if f"c{k}_{key}_full" in Z:
@@ -194,9 +194,13 @@ def test_clip_loss_medium_against_closed_form(B, D, dtype, ls):
     loss.backward(torch.tensor(2.0, device="cuda"))
     tol = TOL[dtype]
     assert abs(float(loss.detach()) - float(ref.loss)) <= tol * abs(float(ref.loss)) + 3e-6
-    assert O.rel_err(a.grad.cpu(), ref.d_image) <= tol
-    assert O.rel_err(b.grad.cpu(), ref.d_text) <= tol
-    assert abs(float(s.grad) - float(ref.d_logit_scale)) <= max(tol, 3e-5) * abs(float(ref.d_logit_scale)) + 1e-6
+    # absolute floor for saturated softmaxes (ls = 100, correlated): s = ls*c is rounded in fp32 (|s| ~ ls), so
+    # G = P_row + P_col - 2E carries ~eps*ls absolute noise; times the gradient's natural scale go*ls/(2B)*sqrt(B)
+    floor = 8 * 1.2e-7 * max(1.0, ls) * 2.0 * ls / (2 * B) * B ** 0.5
+    for got, want in ((a.grad, ref.d_image), (b.grad, ref.d_text)):
+        assert float((got.cpu().double() - want).norm()) <= tol * float(want.norm()) + floor
+    assert abs(float(s.grad) - float(ref.d_logit_scale)) <= max(tol, 3e-5) * abs(float(ref.d_logit_scale)) + \
+        1.2e-7 * 2.0 * max(1.0, ls) * 4
 
 
 def test_symmetry_and_homogeneity_properties():

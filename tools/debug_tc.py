@@ -55,7 +55,7 @@ def run_case(kind, M, N, D, ls, diag_off, dtype, oracle):
               f" nan={int(torch.isnan(af).sum())}")
         if oracle:
             ref, _ = O.block_grad(x.float(), y.float(), ls, lx.cpu(), ly.cpu(), diag_off, 1.0, 1.0, 2.0, 2.0 * ls * 0.5 / M)
-            print(f"  vs fp64 oracle: tc rel={O.rel_err(a.cpu(), ref):.3e}  simt rel={O.rel_err(b.cpu(), ref):.3e}  (kernel: {'1-CTA' if os.environ.get('MCLIP_BWD_1CTA') == '1' else 'CTA pair'})")
+            print(f"  vs fp64 oracle: tc rel={O.rel_err(a.cpu(), ref):.3e}  simt rel={O.rel_err(b.cpu(), ref):.3e}  (kernel: {'1-CTA' if os.environ.get('MCLIP_BWD_1CTA') == '1' else 'CTA pair x' + os.environ.get('MCLIP_BWD_PAIRS', '2')})")
         if rel > 5e-3 or torch.isnan(af).any():
             err = (af - bf).abs()
             rows = err.max(dim=1).values
@@ -100,7 +100,8 @@ CASES = [
     ("bwd", 128, 128, 64, 10.0, 0), ("bwd", 128, 128, 256, 10.0, 0), ("bwd", 128, 128, 512, 14.2857, 0),
     ("bwd", 128, 256, 512, 14.2857, 0), ("bwd", 129, 300, 512, 30.0, 64), ("bwd", 512, 4096, 512, 30.0, 1024),
     ("bwd", 300, 1000, 768, 30.0, 17), ("bwd", 64, 64, 64, 14.2857, 0), ("bwd", 1000, 3000, 384, 14.2857, 100), ("bwd", 2048, 2048, 512, 14.2857, 0),
-    ("bwd_1cta", 128, 128, 512, 14.2857, 0), ("bwd_1cta", 512, 4096, 512, 30.0, 1024),
+    ("bwd_p1", 512, 4096, 512, 30.0, 1024), ("bwd_p1", 1000, 3000, 384, 14.2857, 100),
+    ("bwd", 4096, 4096, 512, 14.2857, 0), ("bwd", 640, 1111, 200, 14.2857, 300),
 ]
 TIMES = [("fwd", 8192, 8192, 512), ("bwd", 8192, 8192, 512), ("fwd", 32768, 32768, 512), ("bwd", 32768, 32768, 512)]
 
@@ -108,6 +109,7 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--one", nargs="*")
     ap.add_argument("--no-time", action="store_true")
+    ap.add_argument("--dbg-sweep", action="store_true")
     args = ap.parse_args()
     if args.one:
         a = args.one
@@ -115,6 +117,14 @@ if __name__ == "__main__":
             time_case(a[1], int(a[2]), int(a[3]), int(a[4]), "bf16", 5)
         else:
             run_case(a[0], int(a[1]), int(a[2]), int(a[3]), float(a[4]), int(a[5]), "bf16", int(a[1]) * int(a[2]) <= 1 << 22)
+        sys.exit(0)
+    if args.dbg_sweep:
+        for pairs in ("1", "2"):
+            for dbg in (0, 6, 2, 4):
+                env = dict(os.environ, MCLIP_DBG=str(dbg), MCLIP_BWD_PAIRS=pairs)
+                r = subprocess.run([sys.executable, __file__, "--one", "time", "bwd", "32768", "32768", "512"], capture_output=True,
+                                   text=True, timeout=150, env=env)
+                print(f"PAIRS={pairs} MCLIP_DBG={dbg}:", r.stdout.strip(), r.stderr[-300:] if r.returncode else "", flush=True)
         sys.exit(0)
     jobs = [[c[0]] + [str(v) for v in c[1:]] for c in CASES]
     if not args.no_time:
@@ -126,6 +136,9 @@ if __name__ == "__main__":
         if j[0].endswith("_1cta"):
             j = [j[0][:-5]] + j[1:]
             env["MCLIP_BWD_1CTA"] = "1"
+        if j[0].endswith("_p1"):
+            j = [j[0][:-3]] + j[1:]
+            env["MCLIP_BWD_PAIRS"] = "1"
         try:
             r = subprocess.run([sys.executable, __file__, "--one"] + j, capture_output=True, text=True, timeout=150, env=env)
             out = (r.stdout + ("\n[stderr] " + r.stderr[-1500:] if r.returncode != 0 else "")).strip()
