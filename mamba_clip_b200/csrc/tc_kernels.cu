@@ -10,6 +10,7 @@
 // warps 4..11 = epilogue (two warpgroups; warp w reads TMEM lanes 32*(w%4).. and one column half).
 #include <cuda.h>
 
+#include <cstdio>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -43,6 +44,7 @@ struct FwdParams {
   float* part_s;
   float* diag;
   int bf16;
+  int dbg;            // development switch (MCLIP_DBG & 16): print barrier-wait cycle counts of a few CTAs
 };
 
 struct BwdParams {
@@ -258,6 +260,190 @@ tc_row_lse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 }
 
 // =================================================================================================
+// forward, CTA-pair version (D <= 512): cta_group::2 MMAs with M = 256 (128 rows per CTA), N = 256.
+// Each CTA streams only its half of the Y tile (the pair shares the N operand), which halves the bytes an SM has
+// to ingest per flop -- the single-CTA kernel needs ~62 B/clk/SM, right at the measured L2->SM limit.
+// =================================================================================================
+constexpr int kFwd2Stages = 6;
+
+template <bool kUnused = true>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_row_lse2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, const FwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr int BN = 256;
+  const uint32_t smem_base = align1024(smem_u32(smem_raw));
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t x_bytes = 8 * kChunkBytes;                       // [8][128 rows][64 k]
+  const uint32_t ring_base = smem_base + x_bytes;                 // [kFwd2Stages][128 y][64 k]
+  const uint32_t misc_base = ring_base + kFwd2Stages * kChunkBytes;
+  uint8_t* misc_gen = smem_gen + (misc_base - smem_base);
+  float2* merge = reinterpret_cast<float2*>(misc_gen);
+  const uint32_t bar_base = misc_base + 1024;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };                 // leader
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };  // per CTA (multicast commit)
+  const uint32_t xfull_bar = bar_base + 8u * (2 * kMaxStages);               // leader
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * kMaxStages + 1 + b); };   // per CTA (multicast commit)
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * kMaxStages + 3 + b); };  // leader: 16 epilogue warps
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 5);
+  uint32_t* tmem_slot_gen = reinterpret_cast<uint32_t*>(misc_gen + 1024 + 8u * (2 * kMaxStages + 5));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int64_t m0 = (int64_t)(blockIdx.x >> 1) * 256 + 128 * rank;
+  const int t0 = blockIdx.y * p.tiles_per_split;
+  const int t1 = min(p.tiles_total, t0 + p.tiles_per_split);
+  const int ntiles = t1 - t0;
+  constexpr uint32_t kTmemCols = 512;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmY);
+    for (int s = 0; s < kFwd2Stages; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
+    mbar_init(xfull_bar, 2);
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 2 * (kEpiThreads / 32)); }
+    fence_barrier_init();
+  } else if (warp == 2) {
+    tmem_alloc_cg2(tmem_slot, kTmemCols);
+    tmem_relinquish_cg2();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      if (leader) mbar_expect_tx(xfull_bar, 2 * x_bytes); else mbar_arrive_cluster(xfull_bar, 0);
+      for (int c = 0; c < 8; ++c) tma_load_2d_cg2(smem_base + c * kChunkBytes, &tmX, c * 64, (int32_t)m0, xfull_bar);
+      uint32_t it = 0;
+      for (int t = t0; t < t1; ++t) {
+        const int32_t y0 = t * BN + 128 * (int32_t)rank;     // this CTA's half of the tile's Y rows
+        for (int c = 0; c < p.kch; ++c, ++it) {
+          const int s = it % kFwd2Stages;
+          const uint32_t ph = (it / kFwd2Stages) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1);
+          if (leader) mbar_expect_tx(full_bar(s), 2 * kChunkBytes); else mbar_arrive_cluster(full_bar(s), 0);
+          tma_load_2d_cg2(ring_base + s * kChunkBytes, &tmY, c * 64, y0, full_bar(s));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      const uint32_t idesc = make_idesc_f16(p.bf16 != 0, p.bf16 != 0, 256, BN, false, false);
+      mbar_wait(xfull_bar, 0);
+      uint32_t it = 0;
+      const bool prof = (p.dbg & 16) != 0;
+      long long t_full = 0, t_tempty = 0, t_begin = clock64();
+      for (int lt = 0; lt < ntiles; ++lt) {
+        const int buf = lt & 1;
+        const uint32_t bph = (lt >> 1) & 1;
+        {
+          const long long t0 = prof ? clock64() : 0;
+          mbar_wait(tempty_bar(buf), bph ^ 1);
+          if (prof) t_tempty += clock64() - t0;
+        }
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * BN;
+        for (int c = 0; c < p.kch; ++c, ++it) {
+          const int s = it % kFwd2Stages;
+          const uint32_t ph = (it / kFwd2Stages) & 1;
+          {
+            const long long t0 = prof ? clock64() : 0;
+            mbar_wait(full_bar(s), ph);
+            if (prof) t_full += clock64() - t0;
+          }
+          tc_fence_after();
+          const uint32_t b_addr = ring_base + s * kChunkBytes;
+          const uint32_t a_addr = smem_base + c * kChunkBytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t ad = make_smem_desc_sw128(a_addr + k * 32, 0, 1024);
+            const uint64_t bd = make_smem_desc_sw128(b_addr + k * 32, 0, 1024);
+            mma_ss_cg2(d_tmem, ad, bd, idesc, (c | k) != 0);
+          }
+          mma_commit_cg2(empty_bar(s), 3);
+        }
+        mma_commit_cg2(tfull_bar(buf), 3);
+      }
+      if (prof && blockIdx.x < 4 && blockIdx.y == 0)
+        printf("[fwd mma cta %d] tiles=%d total=%lld clk wait_full=%lld wait_tempty=%lld (per tile: total %lld full %lld tempty %lld)\n",
+               (int)blockIdx.x, ntiles, clock64() - t_begin, t_full, t_tempty, (clock64() - t_begin) / max(ntiles, 1),
+               t_full / max(ntiles, 1), t_tempty / max(ntiles, 1));
+    }
+  } else if (warp >= kEpiWarp0) {
+    const int ew = warp - kEpiWarp0;
+    const int q = warp & 3;
+    const int half = ew >> 2;
+    const int row_in_tile = q * 32 + lane;
+    const int64_t row = m0 + row_in_tile;
+    const float k2 = p.ls[0] * kLog2e;
+    const int64_t jd = row + p.diag_off;
+    float m2 = -INFINITY, sum = 0.f, diag_val = 0.f;
+    constexpr int kHalfCols = BN / 2;
+    const bool eprof = (p.dbg & 16) != 0 && warp == kEpiWarp0 && lane == 0;
+    long long e_wait = 0, e_begin = clock64();
+    for (int lt = 0; lt < ntiles; ++lt) {
+      const int buf = lt & 1;
+      const uint32_t bph = (lt >> 1) & 1;
+      const int64_t n0 = (int64_t)(t0 + lt) * BN;
+      {
+        const long long tt = eprof ? clock64() : 0;
+        mbar_wait(tfull_bar(buf), bph);
+        if (eprof) e_wait += clock64() - tt;
+      }
+      tc_fence_after();
+      const bool special = (n0 + BN > p.N) || (p.diag != nullptr && n0 < m0 + p.diag_off + 128 && n0 + BN > m0 + p.diag_off);
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + half * kHalfCols;
+#pragma unroll 1
+      for (int cc = 0; cc < kHalfCols / 32; ++cc) {
+        uint32_t v[32];
+        tmem_ld32(t_addr + cc * 32, v);
+        tmem_ld_wait();
+        const int64_t col0 = n0 + half * kHalfCols + cc * 32;
+        if (special) {
+          if (col0 < p.N) fwd_chunk<true>(v, k2, col0, p.N, jd, m2, sum, diag_val);
+        } else {
+          fwd_chunk<false>(v, k2, col0, p.N, jd, m2, sum, diag_val);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(tempty_bar(buf)); else mbar_arrive_cluster(tempty_bar(buf), 0);
+      }
+    }
+    if (eprof && blockIdx.x < 4 && blockIdx.y == 0)
+      printf("[fwd epi cta %d] total=%lld clk wait_tfull=%lld (per tile: total %lld wait %lld)\n", (int)blockIdx.x,
+             clock64() - e_begin, e_wait, (clock64() - e_begin) / max(ntiles, 1), e_wait / max(ntiles, 1));
+    if (half == 1) merge[row_in_tile] = make_float2(m2, sum);
+    named_bar_sync(1, kEpiThreads);
+    if (half == 0) {
+      const float2 o = merge[row_in_tile];
+      const float mm = fmaxf(m2, o.x);
+      float s = 0.f;
+      if (m2 > -INFINITY) s += sum * exp2f(m2 - mm);
+      if (o.x > -INFINITY) s += o.y * exp2f(o.x - mm);
+      if (row < p.M) {
+        p.part_m2[(int64_t)blockIdx.y * p.M + row] = mm;
+        p.part_s[(int64_t)blockIdx.y * p.M + row] = s;
+      }
+    }
+    if (p.diag != nullptr && row < p.M && jd >= 0 && jd < p.N) {
+      const int64_t c_lo = (int64_t)t0 * BN, c_hi = (int64_t)t1 * BN;
+      if (jd >= c_lo && jd < c_hi && (int)((jd % BN) / kHalfCols) == half) p.diag[row] = diag_val;
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_cg2(tmem_base, kTmemCols);
+  }
+}
+
+// =================================================================================================
 // backward
 // =================================================================================================
 // TMEM columns: S/G buffers [0,128) and [128,256); dX accumulator [256, 512).
@@ -287,11 +473,12 @@ __device__ __forceinline__ void bwd_chunk(const uint32_t (&v)[32], uint32_t (&g)
   }
 }
 
-// Single-CTA version (any D <= 768; used for D > 512).  kGF16: G is written as f16 scaled by 2^12; only legal when
-// Y is f16 too (tcgen05 kind::f16 raises an illegal-instruction fault for A = f16, B = bf16 -- measured).
+// Single-CTA version (any D <= 768; used for D > 512).  kGF16: G is written as f16 scaled by 2^12 and the dX MMA
+// reads the f16 copy of Y (tcgen05 kind::f16 raises an illegal-instruction fault for A = f16, B = bf16 -- measured).
 template <bool kBF16, bool XRES, bool kGF16>
 __global__ void __launch_bounds__(kThreads, 1)
-tc_block_grad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
+tc_block_grad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
+                     const __grid_constant__ CUtensorMap tmY16, const BwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = align1024(smem_u32(smem_raw));
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -370,14 +557,15 @@ tc_block_grad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         // Y rows of this step again, as the [K = y][N = d] operand of the dX MMA (single buffer)
         mbar_wait(ydempty_bar, (ls_ & 1) ^ 1);
         mbar_expect_tx(ydfull_bar, (uint32_t)ndc * kChunkBytes);
-        for (int qd = 0; qd < ndc; ++qd) tma_load_2d(yd_base + qd * kChunkBytes, &tmY, (dc0 + qd) * 64, n0, ydfull_bar);
+        for (int qd = 0; qd < ndc; ++qd) tma_load_2d(yd_base + qd * kChunkBytes, &tmY16, (dc0 + qd) * 64, n0, ydfull_bar);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ---------------- MMA issuer ----------------
       const uint32_t idesc_s = make_idesc_f16(kBF16, kBF16, 128, 128, false, false);
-      const uint32_t idesc_dx = make_idesc_f16(kBF16 && !kGF16, kBF16, 128, (uint32_t)ndc * 64, false, true);
+      // with kGF16 both dX operands are f16: G, and the f16 copy of Y behind tmY16
+      const uint32_t idesc_dx = make_idesc_f16(kBF16 && !kGF16, kBF16 && !kGF16, 128, (uint32_t)ndc * 64, false, true);
       if (XRES) mbar_wait(xfull_bar, 0);
       uint32_t it = 0;
       auto issue_s = [&](int ls_) {
@@ -609,6 +797,9 @@ struct Bwd2Params {
   const float* go;
   const float* lse_x;
   const float* ly2;     // [steps_total * 256] lse_y in log2 units, weight and G scale folded, +inf padded; null if w_col == 0
+  const float* bcol;    // [steps_total * 256] 2^(mu0 - ly2[j]) (0 in the padding): column factor of the one-exp path
+  const float* stepmm;  // [steps_total][2] min / max of ly2 over each 256-column step (valid columns only)
+  const float* mu0;     // [1] midpoint of the ly2 range
   float w_row, w_diag, inv_2n;
   int has_col;
   void* dX;
@@ -616,7 +807,7 @@ struct Bwd2Params {
   float* acc_ws;
   float* rd_ws;
   float* rowdot;
-  int dbg;              // development switches (MCLIP_DBG): 1 = epilogue without math, 2 = no S MMAs, 4 = no dX MMAs
+  int dbg;              // development switches (MCLIP_DBG): 1 = epilogue without math, 2 = no S MMAs, 4 = no dX MMAs, 8 = always two exps
 };
 
 constexpr uint32_t kTile8K = 64 * 64 * 2;     // [64 rows x 64 k]
@@ -659,6 +850,38 @@ __device__ __forceinline__ void bwd2_chunk(const uint32_t (&v)[32], uint32_t (&g
 // kPairs = 2: a cluster of four CTAs = two pairs working on adjacent 128-row blocks.  Both pairs need the same Y
 // tiles, so each CTA issues half of the TMA boxes and multicasts them to its counterpart in the other pair:
 // L2 -> SM traffic per flop halves (the pair kernel alone streams 62 B/clk/SM, at the measured L2 limit).
+// One exponential per element: P^col_ij = P^row_ij * 2^(lx2_i - ly2_j) = P^row_ij * a_i * b_j, so
+// G = P^row (1 + a_i b_j).  Only used when the caller has checked that a_i, b_j and a_i * b_j stay finite
+// (|lx2_i - ly2_j| <= 100 over the tile); otherwise bwd2_chunk evaluates both exponentials.
+template <bool kMasked>
+__device__ __forceinline__ void bwd2_chunk_fast(const uint32_t (&v)[32], uint32_t (&g)[16], float k2, float lx2, float a_i,
+                                                const float* __restrict__ bcol, float w_diag_s, int64_t col0, int64_t N,
+                                                int64_t jd, float& rd) {
+  float b[32];
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(bcol + j));
+    b[j] = t.x; b[j + 1] = t.y; b[j + 2] = t.z; b[j + 3] = t.w;
+  }
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    float gv[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const float c = __uint_as_float(v[j + e]);
+      float p_row = ex2_approx(fmaf(c, k2, -lx2));
+      float gg = p_row * fmaf(a_i, b[j + e], 1.f);
+      if (kMasked) {
+        if (col0 + j + e == jd) gg -= w_diag_s;
+        if (col0 + j + e >= N) { gg = 0.f; p_row = 0.f; }
+      }
+      rd = fmaf(p_row, c, rd);
+      gv[e] = gg;
+    }
+    g[j >> 1] = pack_f16x2(gv[0], gv[1]);
+  }
+}
+
 template <bool kBF16, int kPairs>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
@@ -682,6 +905,7 @@ tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   const uint32_t tmem_slot = bar_base + 8u * 16;
   uint32_t* tmem_slot_gen = reinterpret_cast<uint32_t*>(misc_gen + 8u * 16);
   float* rd_scratch = reinterpret_cast<float*>(misc_gen + 256);          // [4][64]
+  float* range_scratch = reinterpret_cast<float*>(misc_gen + 1280);      // [8][2]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = cluster_ctarank();          // 0 .. 2*kPairs-1
@@ -725,10 +949,14 @@ tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       if (leader) mbar_expect_tx(xfull_bar, 2 * 8 * kTile8K); else mbar_arrive_cluster(xfull_bar, leader_rank);
       for (int c = 0; c < 8; ++c) tma_load_2d_cg2(x_base + c * kTile8K, &tmX, c * 64, (int32_t)m0, xfull_bar);
       uint32_t it = 0;
+      const bool pprof = (p.dbg & 16) != 0;
+      long long p_empty = 0, p_begin = clock64();
       auto stage_begin = [&]() -> uint32_t {
         const int s = it % kRing2;
         const uint32_t ph = (it / kRing2) & 1;
+        const long long t0 = pprof ? clock64() : 0;
         mbar_wait(empty_bar(s), ph ^ 1);
+        if (pprof) p_empty += clock64() - t0;
         if (leader) mbar_expect_tx(full_bar(s), 2 * kStage2); else mbar_arrive_cluster(full_bar(s), leader_rank);
         ++it;
         return (uint32_t)s;
@@ -766,6 +994,9 @@ tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         if (st + 1 < nsteps) load_s(st + 1);
         load_dx(st);
       }
+      if (pprof && blockIdx.x < 4 && blockIdx.y == 0)
+        printf("[tma cta %d] total=%lld clk  wait_empty=%lld (per step: total %lld empty %lld)\n", (int)blockIdx.x,
+               clock64() - p_begin, p_empty, (clock64() - p_begin) / max(nsteps, 1), p_empty / max(nsteps, 1));
     }
   } else if (warp == 1) {
     if (lane == 0 && leader) {
@@ -774,10 +1005,14 @@ tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       const uint32_t idesc_dx = make_idesc_f16(false, false, 128, 256, false, true);
       mbar_wait(xfull_bar, 0);
       uint32_t it = 0;
+      const bool prof = (p.dbg & 16) != 0;
+      long long t_full = 0, t_gfull = 0, t_begin = clock64();
       auto stage_wait = [&]() -> uint32_t {
         const int s = it % kRing2;
         const uint32_t ph = (it / kRing2) & 1;
+        const long long t0 = prof ? clock64() : 0;
         mbar_wait(full_bar(s), ph);
+        if (prof) t_full += clock64() - t0;
         tc_fence_after();
         ++it;
         return (uint32_t)s;
@@ -804,7 +1039,11 @@ tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         mma_commit_cg2(sfull_bar(buf), pair_mask);
       };
       auto issue_dx = [&](int st) {
-        mbar_wait(gfull_bar, st & 1);
+        {
+          const long long t0 = prof ? clock64() : 0;
+          mbar_wait(gfull_bar, st & 1);
+          if (prof) t_gfull += clock64() - t0;
+        }
         tc_fence_after();
         for (int yh = 0; yh < 2; ++yh) {
           for (int h = 0; h < p.ndh; ++h) {
@@ -828,6 +1067,10 @@ tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         issue_dx(st);
       }
       mma_commit_cg2(dxfull_bar, pair_mask);
+      if (prof && blockIdx.x < 4 && blockIdx.y == 0)
+        printf("[mma cta %d] steps=%d total=%lld clk  wait_full=%lld  wait_gfull=%lld  (per step: total %lld full %lld gfull %lld)\n",
+               (int)blockIdx.x, nsteps, clock64() - t_begin, t_full, t_gfull, (clock64() - t_begin) / max(nsteps, 1),
+               t_full / max(nsteps, 1), t_gfull / max(nsteps, 1));
     }
   } else if (warp >= kEpiWarp0) {
     // ---------------- epilogue: S -> G (f16 * 2^12) into shared memory; finally dX out ----------------
@@ -841,19 +1084,54 @@ tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     const float ls = p.ls[0];
     const float k2 = ls * kLog2e;
     const bool has_col = p.has_col != 0;
-    const float lx2 = (row < p.M ? p.lse_x[row] * kLog2e : 0.f) - (log2f(p.w_row) + 12.f);
+    // rows past M reuse the last valid row's LSE so that they do not widen the range check below
+    const float lx2 = p.lse_x[row < p.M ? row : p.M - 1] * kLog2e - (log2f(p.w_row) + 12.f);
     const float w_diag_s = p.w_diag * kGScale;
     const int64_t jd = row + p.diag_off;
     float rd = 0.f;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const int64_t blk_lo = pair_row0 + p.diag_off;   // diagonal columns of the pair's rows
+    // one-exp path set-up: a_i and the range of lx2 over this CTA's rows
+    float mu0 = 0.f, a_i = 0.f, lx_min = 0.f, lx_max = 0.f;
+    bool a_ok = false;
+    if (has_col) {
+      mu0 = p.mu0[0];
+      a_i = ex2_approx(lx2 - mu0);
+      float mn = lx2, mx = lx2;
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      }
+      if (lane == 0) { range_scratch[2 * ew] = mn; range_scratch[2 * ew + 1] = mx; }
+      named_bar_sync(1, kEpiThreads);
+      lx_min = range_scratch[0]; lx_max = range_scratch[1];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) {
+        lx_min = fminf(lx_min, range_scratch[2 * w]);
+        lx_max = fmaxf(lx_max, range_scratch[2 * w + 1]);
+      }
+      a_ok = fabsf(lx_max - mu0) <= 120.f && fabsf(lx_min - mu0) <= 120.f;
+    }
+    const bool eprof = (p.dbg & 16) != 0 && warp == kEpiWarp0 && lane == 0;
+    long long e_sfull = 0, e_gempty = 0, e_begin = clock64();
     for (int st = 0; st < nsteps; ++st) {
       const int buf = st & 1;
       const uint32_t bph = (st >> 1) & 1;
       const int64_t n0 = (int64_t)(s0 + st) * 256;
-      mbar_wait(sfull_bar(buf), bph);
+      {
+        const long long t0 = eprof ? clock64() : 0;
+        mbar_wait(sfull_bar(buf), bph);
+        if (eprof) e_sfull += clock64() - t0;
+      }
       tc_fence_after();
       const bool special = (n0 + 256 > p.N) || (n0 < blk_lo + 128 && n0 + 256 > blk_lo);
+      bool fast = false;
+      if (has_col && a_ok && !(p.dbg & 8)) {
+        const float2 mm = __ldg(reinterpret_cast<const float2*>(p.stepmm) + (s0 + st));   // (min, max) of ly2 in this step
+        fast = (lx_max - mm.x <= 100.f) && (mm.y - lx_min <= 100.f) &&
+               (!(mm.x <= mm.y) || (fabsf(mm.x - mu0) <= 120.f && fabsf(mm.y - mu0) <= 120.f));
+      }
       const uint32_t g_row = g_base + kc * kTile8K + r * 128;
       uint32_t g[2][16];
 #pragma unroll
@@ -866,6 +1144,9 @@ tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         if (p.dbg & 1) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) g[cc][j] = v[2 * j] & 0x3c003c00u;
+        } else if (fast) {
+          if (special) bwd2_chunk_fast<true>(v, g[cc], k2, lx2, a_i, p.bcol + col0, w_diag_s, col0, p.N, jd, rd);
+          else bwd2_chunk_fast<false>(v, g[cc], k2, lx2, a_i, p.bcol + col0, w_diag_s, col0, p.N, jd, rd);
         } else if (special) {
           if (has_col) bwd2_chunk<true, true>(v, g[cc], k2, lx2, ly2, w_diag_s, col0, p.N, jd, rd);
           else bwd2_chunk<true, false>(v, g[cc], k2, lx2, ly2, w_diag_s, col0, p.N, jd, rd);
@@ -877,7 +1158,11 @@ tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       tc_fence_before();          // TMEM reads of S are complete
       // G is single-buffered: the dX MMAs of the previous step must have finished reading it.  The values are
       // already in registers, so this wait overlaps with the S MMAs of the next step on the tensor pipe.
-      mbar_wait(gempty_bar, (st & 1) ^ 1);
+      {
+        const long long t0 = eprof ? clock64() : 0;
+        mbar_wait(gempty_bar, (st & 1) ^ 1);
+        if (eprof) e_gempty += clock64() - t0;
+      }
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
         // 32 f16 = four 16-byte pieces (cc*4 .. cc*4+3) of this row's 128-byte line, 128B-swizzled
@@ -893,6 +1178,10 @@ tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         if (leader) mbar_arrive(gfull_bar); else mbar_arrive_cluster(gfull_bar, leader_rank);
       }
     }
+    if (eprof && blockIdx.x < 4 && blockIdx.y == 0)
+      printf("[epi cta %d] total=%lld clk  wait_sfull=%lld  wait_gempty=%lld (per step: total %lld sfull %lld gempty %lld)\n",
+             (int)blockIdx.x, clock64() - e_begin, e_sfull, e_gempty, (clock64() - e_begin) / max(nsteps, 1),
+             e_sfull / max(nsteps, 1), e_gempty / max(nsteps, 1));
     // ---- dX accumulator -> global ----
     mbar_wait(dxfull_bar, 0);
     tc_fence_after();
@@ -964,11 +1253,58 @@ tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   }
 }
 
-// lse_y -> log2 units with the column weight and the G scale folded in, +inf padded to a multiple of 256
-__global__ void prep_ly2_kernel(const float* __restrict__ lse_y, int64_t N, int64_t n_pad, float lw_col,
-                                float* __restrict__ ly2) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n_pad) ly2[i] = i < N ? lse_y[i] * kLog2e - lw_col : INFINITY;
+// Column statistics for the backward kernel (one block of 1024 threads):
+//   ly2[j]  = lse_y[j] * log2e - lw_col              (+inf in the padding up to a multiple of 256)
+//   mu0     = midpoint of the ly2 range;  bcol[j] = 2^(mu0 - ly2[j])  (0 in the padding)
+//   stepmm  = (min, max) of ly2 over each 256-column step
+__global__ void __launch_bounds__(1024)
+prep_ly2_kernel(const float* __restrict__ lse_y, int64_t N, int64_t n_pad, float lw_col, float* __restrict__ ly2,
+                float* __restrict__ bcol, float* __restrict__ stepmm, float* __restrict__ mu0_out) {
+  __shared__ float red_min[32], red_max[32];
+  __shared__ float mu_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float mn = INFINITY, mx = -INFINITY;
+  for (int64_t j = tid; j < N; j += 1024) {
+    const float v = lse_y[j] * kLog2e - lw_col;
+    mn = fminf(mn, v); mx = fmaxf(mx, v);
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if (lane == 0) { red_min[warp] = mn; red_max[warp] = mx; }
+  __syncthreads();
+  if (warp == 0) {
+    mn = red_min[lane]; mx = red_max[lane];
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (lane == 0) { mu_s = 0.5f * mn + 0.5f * mx; mu0_out[0] = mu_s; }
+  }
+  __syncthreads();
+  const float mu = mu_s;
+  const int64_t nsteps = n_pad / 256;
+  for (int64_t st = warp; st < nsteps; st += 32) {
+    float smn = INFINITY, smx = -INFINITY;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int64_t j = st * 256 + e * 32 + lane;
+      const bool ok = j < N;
+      const float v = ok ? lse_y[j] * kLog2e - lw_col : INFINITY;
+      ly2[j] = v;
+      bcol[j] = ok ? exp2f(mu - v) : 0.f;
+      if (ok) { smn = fminf(smn, v); smx = fmaxf(smx, v); }
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      smn = fminf(smn, __shfl_xor_sync(0xffffffffu, smn, o));
+      smx = fmaxf(smx, __shfl_xor_sync(0xffffffffu, smx, o));
+    }
+    if (lane == 0) { stepmm[2 * st] = smn; stepmm[2 * st + 1] = smx; }
+  }
 }
 
 // bf16 -> f16 copy of Y (exact for 6.1e-5 <= |v| <= 65504; saturating above, f16-subnormal below)
@@ -1088,6 +1424,43 @@ FwdPlan plan_fwd(int64_t M, int64_t N, int64_t D) {
   return f;
 }
 
+// MCLIP_FWD_1CTA=1 forces the single-CTA forward kernel also for D <= 512 (development A/B switch).
+bool use_single_cta_fwd() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("MCLIP_FWD_1CTA");
+    cached = (e && e[0] == '1') ? 1 : 0;
+  }
+  return cached == 1;
+}
+
+bool fwd_uses_pair(int64_t D) { return D <= 512 && !use_single_cta_fwd(); }
+
+FwdPlan plan_fwd2(int64_t M, int64_t N, int64_t D) {
+  FwdPlan f;
+  f.kch = (int)ceil_div(D, 64);
+  f.xres = true;
+  f.bn = 256;
+  f.stages = kFwd2Stages;
+  f.tiles_total = (int)ceil_div(N, f.bn);
+  const int64_t pairs = ceil_div(M, 256);
+  int best = 1;
+  double best_cost = 1e30;
+  const int max_split = f.tiles_total < 64 ? f.tiles_total : 64;
+  for (int s = 1; s <= max_split; ++s) {
+    const int tps = (int)ceil_div(f.tiles_total, s);
+    const int real = (int)ceil_div(f.tiles_total, tps);
+    if (real != s) continue;
+    const double waves = (double)ceil_div(pairs * s, 74);
+    const double cost = waves * (tps + 1.5);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
+  }
+  f.nsplit = best;
+  f.tiles_per_split = (int)ceil_div(f.tiles_total, best);
+  f.smem = kAlignSlack + 8 * kChunkBytes + kFwd2Stages * kChunkBytes + kMiscBytes;
+  return f;
+}
+
 struct BwdPlan { bool xres; int stages; int kch; int dchunks; int steps_total; int nsplit; int steps_per_split; uint32_t smem; };
 
 BwdPlan plan_bwd(int64_t M, int64_t N, int64_t D) {
@@ -1121,12 +1494,14 @@ BwdPlan plan_bwd(int64_t M, int64_t N, int64_t D) {
 
 struct Bwd2Plan { int kch; int kpairs; int ndh; int steps_total; int nsplit; int steps_per_split; uint32_t smem; int cpairs; };
 
-// MCLIP_BWD_PAIRS=1 selects clusters of one CTA pair (no multicast); default 2 pairs per cluster.
+// Pairs per cluster.  Default 1: the pair kernel is limited by the ~64 B/clk each SM can ingest from L2, which
+// multicast does not reduce (measured: 1.95 ms with 2 pairs + multicast vs 1.85 ms with 1 pair at 32768^2 x 512,
+// and 4-CTA clusters strand 16 of the 148 SMs).  MCLIP_BWD_PAIRS=2 selects the multicast variant.
 int bwd_cluster_pairs() {
   static int cached = -1;
   if (cached < 0) {
     const char* e = getenv("MCLIP_BWD_PAIRS");
-    cached = (e && e[0] == '1') ? 1 : 2;
+    cached = (e && e[0] == '2') ? 2 : 1;
   }
   return cached;
 }
@@ -1164,7 +1539,7 @@ BwdWs bwd_ws_layout(int nsplit, int64_t M, int64_t N, int64_t D, int64_t n_pad, 
   size_t off = 0;
   w.acc = off; off += nsplit > 1 ? align_up((size_t)nsplit * M * D * sizeof(float), 256) : 0;
   w.rd = off;  off += nsplit > 1 ? align_up((size_t)nsplit * M * sizeof(float), 256) : 0;
-  w.ly2 = off; off += align_up((size_t)n_pad * sizeof(float), 256);
+  w.ly2 = off; off += align_up(((size_t)2 * n_pad + 2 * (n_pad / 256) + 64) * sizeof(float), 256);  // ly2, bcol, stepmm, mu0
   w.y16 = off; off += need_y16 ? align_up((size_t)N * D * 2, 256) : 0;
   w.total = off;
   return w;
@@ -1187,7 +1562,7 @@ bool tc_supported(int64_t M, int64_t N, int64_t D, int64_t ldx, int64_t ldy, int
 }
 
 size_t tc_row_lse_ws(int64_t M, int64_t N, int64_t D) {
-  const FwdPlan f = plan_fwd(M, N, D);
+  const FwdPlan f = fwd_uses_pair(D) ? plan_fwd2(M, N, D) : plan_fwd(M, N, D);
   return align_up((size_t)f.nsplit * M * 2 * sizeof(float), 256);
 }
 
@@ -1198,17 +1573,18 @@ size_t tc_block_grad_ws(int64_t M, int64_t N, int64_t D) {
     return bwd_ws_layout(b.nsplit, M, N, D, (int64_t)b.steps_total * 256, true).total;
   }
   const BwdPlan b = plan_bwd(M, N, D);
-  return b.nsplit > 1 ? align_up((size_t)b.nsplit * M * (D + 1) * sizeof(float), 256) : 0;
+  return (b.nsplit > 1 ? align_up((size_t)b.nsplit * M * (D + 1) * sizeof(float), 256) : 0) + align_up((size_t)N * D * 2, 256);
 }
 
 int tc_row_lse(const RowLseArgs& a) {
   if (((uintptr_t)a.X | (uintptr_t)a.Y) & 15) { set_error("row_lse(tcgen05): X/Y must be 16-byte aligned"); return MCLIP_ERR_INVALID; }
-  const FwdPlan f = plan_fwd(a.M, a.N, a.D);
+  const bool pair = fwd_uses_pair(a.D);
+  const FwdPlan f = pair ? plan_fwd2(a.M, a.N, a.D) : plan_fwd(a.M, a.N, a.D);
   if (f.stages < 2) { set_error("row_lse(tcgen05): not enough shared memory for D=%lld", (long long)a.D); return MCLIP_ERR_UNSUPPORTED; }
   CUtensorMap tmX, tmY;
   int rc = make_tmap(&tmX, a.X, a.M, a.D, a.ldx, a.dtype, 128);
   if (rc) return rc;
-  rc = make_tmap(&tmY, a.Y, a.N, a.D, a.ldy, a.dtype, (uint32_t)f.bn);
+  rc = make_tmap(&tmY, a.Y, a.N, a.D, a.ldy, a.dtype, pair ? 128u : (uint32_t)f.bn);
   if (rc) return rc;
   FwdParams p;
   p.M = a.M; p.N = a.N; p.kch = f.kch; p.stages = f.stages; p.tiles_total = f.tiles_total;
@@ -1216,9 +1592,29 @@ int tc_row_lse(const RowLseArgs& a) {
   p.part_m2 = reinterpret_cast<float*>(a.ws);
   p.part_s = p.part_m2 + (size_t)f.nsplit * a.M;
   p.diag = a.diag; p.bf16 = a.dtype == MCLIP_DTYPE_BF16;
+  {
+    const char* e = getenv("MCLIP_DBG");
+    p.dbg = e ? atoi(e) : 0;
+  }
   if (a.diag) MCLIP_CUDA_OK(cudaMemsetAsync(a.diag, 0, sizeof(float) * a.M, a.stream));
   dim3 grid((unsigned)ceil_div(a.M, 128), (unsigned)f.nsplit);
-  if (f.xres) {
+  if (pair) {
+    rc = set_smem(tc_row_lse2_kernel<true>, f.smem);
+    if (rc) return rc;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * ceil_div(a.M, 256)), (unsigned)f.nsplit);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = f.smem;
+    cfg.stream = a.stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MCLIP_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_row_lse2_kernel<true>, tmX, tmY, p));
+  } else if (f.xres) {
     rc = set_smem(tc_row_lse_kernel<256, true>, f.smem);
     if (rc) return rc;
     tc_row_lse_kernel<256, true><<<grid, kThreads, f.smem, a.stream>>>(tmX, tmY, p);
@@ -1241,9 +1637,12 @@ int tc_block_grad2(const BlockGradArgs& a) {
   if (w.total > a.ws_bytes) { set_error("block_grad(tcgen05): workspace %zu < %zu", a.ws_bytes, w.total); return MCLIP_ERR_WORKSPACE; }
   uint8_t* ws = reinterpret_cast<uint8_t*>(a.ws);
   float* ly2 = reinterpret_cast<float*>(ws + w.ly2);
+  float* bcol = ly2 + n_pad;
+  float* stepmm = bcol + n_pad;
+  float* mu0 = stepmm + 2 * (n_pad / 256);
   const bool has_col = a.w_col != 0.f;
   if (has_col) {
-    prep_ly2_kernel<<<(unsigned)ceil_div(n_pad, 256), 256, 0, a.stream>>>(a.lse_y, a.N, n_pad, log2f(a.w_col) + 12.f, ly2);
+    prep_ly2_kernel<<<1, 1024, 0, a.stream>>>(a.lse_y, a.N, n_pad, log2f(a.w_col) + 12.f, ly2, bcol, stepmm, mu0);
     count_launch();
     MCLIP_CUDA_OK(cudaGetLastError());
   }
@@ -1269,7 +1668,7 @@ int tc_block_grad2(const BlockGradArgs& a) {
   Bwd2Params p;
   p.M = a.M; p.N = a.N; p.D = a.D; p.kpairs = b.kpairs; p.ndh = b.ndh; p.steps_total = b.steps_total;
   p.steps_per_split = b.steps_per_split; p.nsplit = b.nsplit; p.diag_off = a.diag_off; p.ls = a.logit_scale;
-  p.go = a.grad_out; p.lse_x = a.lse_x; p.ly2 = has_col ? ly2 : nullptr; p.w_row = a.w_row; p.w_diag = a.w_diag;
+  p.go = a.grad_out; p.lse_x = a.lse_x; p.ly2 = has_col ? ly2 : nullptr; p.bcol = bcol; p.stepmm = stepmm; p.mu0 = mu0; p.w_row = a.w_row; p.w_diag = a.w_diag;
   p.inv_2n = a.inv_2n; p.has_col = has_col ? 1 : 0; p.dX = a.dX; p.lddx = a.lddx;
   p.acc_ws = reinterpret_cast<float*>(ws + w.acc); p.rd_ws = reinterpret_cast<float*>(ws + w.rd); p.rowdot = a.rowdot;
   {
@@ -1325,10 +1724,27 @@ int tc_block_grad(const BlockGradArgs& a) {
   if (a.D <= 512 && !use_single_cta_bwd()) return tc_block_grad2(a);
   const BwdPlan b = plan_bwd(a.M, a.N, a.D);
   if (b.stages < 2) { set_error("block_grad(tcgen05): not enough shared memory for D=%lld", (long long)a.D); return MCLIP_ERR_UNSUPPORTED; }
-  CUtensorMap tmX, tmY;
-  int rc = make_tmap(&tmX, a.X, a.M, a.D, a.ldx, a.dtype, 128);
+  const bool bf = a.dtype == MCLIP_DTYPE_BF16;
+  const size_t acc_bytes = b.nsplit > 1 ? align_up((size_t)b.nsplit * a.M * (a.D + 1) * sizeof(float), 256) : 0;
+  const void* y16 = a.Y;
+  int64_t ld16 = a.ldy;
+  int rc;
+  if (bf) {
+    __half* dst = reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(a.ws) + acc_bytes);
+    const int64_t n8 = a.N * (a.D / 8);
+    const unsigned blocks = (unsigned)(ceil_div(n8, 256) < 148 * 8 ? ceil_div(n8, 256) : 148 * 8);
+    bf16_to_f16_kernel<<<blocks, 256, 0, a.stream>>>(reinterpret_cast<const __nv_bfloat16*>(a.Y), a.N, a.D, a.ldy, dst);
+    count_launch();
+    MCLIP_CUDA_OK(cudaGetLastError());
+    y16 = dst;
+    ld16 = a.D;
+  }
+  CUtensorMap tmX, tmY, tmY16;
+  rc = make_tmap(&tmX, a.X, a.M, a.D, a.ldx, a.dtype, 128);
   if (rc) return rc;
   rc = make_tmap(&tmY, a.Y, a.N, a.D, a.ldy, a.dtype, 128);
+  if (rc) return rc;
+  rc = make_tmap(&tmY16, y16, a.N, a.D, ld16, MCLIP_DTYPE_F16, 128);
   if (rc) return rc;
   BwdParams p;
   p.M = a.M; p.N = a.N; p.D = a.D; p.kch = b.kch; p.stages = b.stages; p.steps_total = b.steps_total;
@@ -1338,13 +1754,12 @@ int tc_block_grad(const BlockGradArgs& a) {
   p.acc_ws = reinterpret_cast<float*>(a.ws); p.rowdot = a.rowdot;
   p.rd_ws = p.acc_ws + (size_t)b.nsplit * a.M * a.D;
   dim3 grid((unsigned)ceil_div(a.M, 128), (unsigned)b.dchunks, (unsigned)b.nsplit);
-  const bool bf = a.dtype == MCLIP_DTYPE_BF16;
-  const bool g_bf16 = bf;   // kind::f16 needs A and B in the same format: G follows the inputs on this path
+  const bool g_bf16 = false;   // G is always f16 * 2^12; bf16 inputs go through the f16 copy of Y
 #define MCLIP_LAUNCH_BWD(BF, XR, GF)                                                          \
   do {                                                                                        \
     rc = set_smem(tc_block_grad_kernel<BF, XR, GF>, b.smem);                                  \
     if (rc) return rc;                                                                        \
-    tc_block_grad_kernel<BF, XR, GF><<<grid, kThreads, b.smem, a.stream>>>(tmX, tmY, p);      \
+    tc_block_grad_kernel<BF, XR, GF><<<grid, kThreads, b.smem, a.stream>>>(tmX, tmY, tmY16, p); \
   } while (0)
   if (bf && b.xres && !g_bf16) MCLIP_LAUNCH_BWD(true, true, true);
   else if (bf && b.xres) MCLIP_LAUNCH_BWD(true, true, false);

@@ -100,7 +100,8 @@ CASES = [
     ("bwd", 128, 128, 64, 10.0, 0), ("bwd", 128, 128, 256, 10.0, 0), ("bwd", 128, 128, 512, 14.2857, 0),
     ("bwd", 128, 256, 512, 14.2857, 0), ("bwd", 129, 300, 512, 30.0, 64), ("bwd", 512, 4096, 512, 30.0, 1024),
     ("bwd", 300, 1000, 768, 30.0, 17), ("bwd", 64, 64, 64, 14.2857, 0), ("bwd", 1000, 3000, 384, 14.2857, 100), ("bwd", 2048, 2048, 512, 14.2857, 0),
-    ("bwd_p1", 512, 4096, 512, 30.0, 1024), ("bwd_p1", 1000, 3000, 384, 14.2857, 100),
+    ("bwd_p2", 512, 4096, 512, 30.0, 1024), ("bwd_2exp", 1000, 3000, 384, 14.2857, 100),
+    ("fwd", 256, 256, 512, 14.2857, 0), ("fwd", 2048, 2048, 512, 100.0, 0), ("fwd", 1000, 3000, 384, 14.2857, 100),
     ("bwd", 4096, 4096, 512, 14.2857, 0), ("bwd", 640, 1111, 200, 14.2857, 300),
 ]
 TIMES = [("fwd", 8192, 8192, 512), ("bwd", 8192, 8192, 512), ("fwd", 32768, 32768, 512), ("bwd", 32768, 32768, 512)]
@@ -119,12 +120,14 @@ if __name__ == "__main__":
             run_case(a[0], int(a[1]), int(a[2]), int(a[3]), float(a[4]), int(a[5]), "bf16", int(a[1]) * int(a[2]) <= 1 << 22)
         sys.exit(0)
     if args.dbg_sweep:
-        for pairs in ("1", "2"):
-            for dbg in (0, 6, 2, 4):
-                env = dict(os.environ, MCLIP_DBG=str(dbg), MCLIP_BWD_PAIRS=pairs)
-                r = subprocess.run([sys.executable, __file__, "--one", "time", "bwd", "32768", "32768", "512"], capture_output=True,
+        for kind, extra in (("bwd", {"MCLIP_DBG": "0"}), ("bwd", {"MCLIP_DBG": "8"}), ("bwd", {"MCLIP_DBG": "1"}),
+                            ("bwd", {"MCLIP_DBG": "0", "MCLIP_BWD_PAIRS": "2"}),
+                            ("fwd", {}), ("fwd", {"MCLIP_FWD_1CTA": "1"})):
+            env = dict(os.environ, **extra)
+            for shape in (("32768", "32768", "512"), ("4096", "32768", "512")):
+                r = subprocess.run([sys.executable, __file__, "--one", "time", kind, *shape], capture_output=True,
                                    text=True, timeout=150, env=env)
-                print(f"PAIRS={pairs} MCLIP_DBG={dbg}:", r.stdout.strip(), r.stderr[-300:] if r.returncode else "", flush=True)
+                print(f"{extra}:", r.stdout.strip(), r.stderr[-300:] if r.returncode else "", flush=True)
         sys.exit(0)
     jobs = [[c[0]] + [str(v) for v in c[1:]] for c in CASES]
     if not args.no_time:
@@ -136,9 +139,12 @@ if __name__ == "__main__":
         if j[0].endswith("_1cta"):
             j = [j[0][:-5]] + j[1:]
             env["MCLIP_BWD_1CTA"] = "1"
-        if j[0].endswith("_p1"):
+        if j[0].endswith("_p2"):
             j = [j[0][:-3]] + j[1:]
-            env["MCLIP_BWD_PAIRS"] = "1"
+            env["MCLIP_BWD_PAIRS"] = "2"
+        if j[0].endswith("_2exp"):
+            j = [j[0][:-5]] + j[1:]
+            env["MCLIP_DBG"] = "8"
         try:
             r = subprocess.run([sys.executable, __file__, "--one"] + j, capture_output=True, text=True, timeout=150, env=env)
             out = (r.stdout + ("\n[stderr] " + r.stderr[-1500:] if r.returncode != 0 else "")).strip()
