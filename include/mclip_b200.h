@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MCLIP_ABI_VERSION 1
+#define MCLIP_ABI_VERSION 2
 
 enum { MCLIP_DTYPE_F32 = 0, MCLIP_DTYPE_BF16 = 1, MCLIP_DTYPE_F16 = 2 };
 enum { MCLIP_PATH_AUTO = 0, MCLIP_PATH_SIMT = 1, MCLIP_PATH_TCGEN05 = 2 };
@@ -56,13 +56,14 @@ int mclip_workspace_bytes(int64_t M, int64_t N, int64_t D, int dtype, int op, in
  *   S = logit_scale * X @ Y^T            X: [M, D] (ldx), Y: [N, D] (ldy), row-major
  *   lse[i]  = log sum_j exp(S[i, j])                          (natural log, f32)
  *   diag[i] = <X[i], Y[i + diag_off]>  (raw dot product, 0 when i + diag_off is outside [0, N))
+ *   rowdot[i] = sum_j softmax_j(S[i, :]) * <X[i], Y[j]>       (f32; feeds d logit_scale, see mclip_dls_finalize)
  * Replaces, for one side of the loss, reference loss.py:102-111 (`logit_scale * a @ b.T`) fused with
  * the log_softmax half of F.cross_entropy at loss.py:143-144; `diag_off` is the label offset of
  * loss.py:80-81 (`labels + num_logits * rank`).  Called twice per forward: (image rows, all text) and
- * (text rows, all image).  `logit_scale` is a device scalar (no host sync).  `diag` may be NULL.
+ * (text rows, all image).  `logit_scale` is a device scalar (no host sync).  `diag` and `rowdot` may be NULL.
  */
 int mclip_row_lse(const void* X, const void* Y, int64_t M, int64_t N, int64_t D, int64_t ldx, int64_t ldy,
-                  int dtype, const float* logit_scale, int64_t diag_off, float* lse, float* diag,
+                  int dtype, const float* logit_scale, int64_t diag_off, float* lse, float* diag, float* rowdot,
                   void* ws, size_t ws_bytes, int path, void* cuda_stream);
 
 /*
@@ -70,7 +71,7 @@ int mclip_row_lse(const void* X, const void* Y, int64_t M, int64_t N, int64_t D,
  *   s_ij  = logit_scale * <X[i], Y[j]>
  *   G_ij  = w_row * exp(s_ij - lse_x[i]) + w_col * exp(s_ij - lse_y[j]) - w_diag * [j == i + diag_off]
  *   dX    = (grad_out * logit_scale * inv_2n) * G @ Y          written in the input dtype, [M, D] (lddx)
- *   rowdot[i] = sum_j exp(s_ij - lse_x[i]) * <X[i], Y[j]>      (f32; feeds d logit_scale)
+ *   rowdot[i] = sum_j exp(s_ij - lse_x[i]) * <X[i], Y[j]>      (f32; same quantity mclip_row_lse can emit)
  * Replaces the implicit autograd graph of loss.py:102-111,142-145 (MmBackward + LogSoftmaxBackward +
  * NllLossBackward) for one side.  `lse_y` may be NULL iff w_col == 0 (local_loss without
  * gather_with_grad: own-row terms only).  `grad_out` is a device scalar (GradScaler's scale reaches

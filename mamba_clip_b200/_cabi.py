@@ -15,7 +15,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmclip_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 DTYPE_CODES = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
 PATH_AUTO, PATH_SIMT, PATH_TCGEN05 = 0, 1, 2
 OP_ROW_LSE, OP_BLOCK_GRAD = 0, 1
@@ -29,8 +29,8 @@ _SIGNATURES = {
     "mclip_select_path": (ctypes.c_int, [ctypes.c_int64] * 5 + [ctypes.c_int, ctypes.c_int]),
     "mclip_workspace_bytes": (ctypes.c_int, [ctypes.c_int64] * 3 + [ctypes.c_int] * 3 + [ctypes.POINTER(ctypes.c_size_t)]),
     "mclip_row_lse": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int64] * 5 + [ctypes.c_int, _c_f32p,
-                                     ctypes.c_int64, _c_f32p, _c_f32p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
-                                     ctypes.c_void_p]),
+                                     ctypes.c_int64, _c_f32p, _c_f32p, _c_f32p, ctypes.c_void_p, ctypes.c_size_t,
+                                     ctypes.c_int, ctypes.c_void_p]),
     "mclip_block_grad": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int64] * 5 + [ctypes.c_int, _c_f32p,
                                         _c_f32p, _c_f32p, _c_f32p, ctypes.c_int64] + [ctypes.c_float] * 4 +
                          [ctypes.c_void_p, ctypes.c_int64, _c_f32p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
@@ -119,20 +119,22 @@ class CudaBackend:
         return int(self.lib.mclip_launch_count())
 
     # -- ops -------------------------------------------------------------------------------------
-    def row_lse(self, X: torch.Tensor, Y: torch.Tensor, ls: torch.Tensor, diag_off: int,
-                want_diag: bool) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    def row_lse(self, X: torch.Tensor, Y: torch.Tensor, ls: torch.Tensor, diag_off: int, want_diag: bool,
+                want_rowdot: bool = False):
+        """-> (lse, diag or None) or, with want_rowdot, (lse, diag or None, rowdot)."""
         dev = self._prep(X, Y, ls)
         M, D = X.shape
         N = Y.shape[0]
         lse = torch.empty(M, dtype=torch.float32, device=dev)
         diag = torch.empty(M, dtype=torch.float32, device=dev) if want_diag else None
+        rowdot = torch.empty(M, dtype=torch.float32, device=dev) if want_rowdot else None
         ws, nws = self._workspace(M, N, D, X.dtype, OP_ROW_LSE, dev)
         with torch.cuda.device(dev):
             rc = self.lib.mclip_row_lse(_ptr(X), _ptr(Y), M, N, D, X.stride(0), Y.stride(0), DTYPE_CODES[X.dtype],
-                                        _ptr(ls), diag_off, _ptr(lse), _ptr(diag), _ptr(ws), nws, self.path,
-                                        self._stream(dev))
+                                        _ptr(ls), diag_off, _ptr(lse), _ptr(diag), _ptr(rowdot), _ptr(ws), nws,
+                                        self.path, self._stream(dev))
         _check(self.lib, rc, "mclip_row_lse")
-        return lse, diag
+        return (lse, diag, rowdot) if want_rowdot else (lse, diag)
 
     def block_grad(self, X, Y, ls, go, lse_x, lse_y, diag_off, w_row, w_col, w_diag, inv_2n, want_rowdot=True):
         dev = self._prep(X, Y, ls, lse_x)

@@ -25,13 +25,20 @@ from . import _cabi
 _SUPPORTED = (torch.float32, torch.bfloat16, torch.float16)
 
 
-def _gather_rows(x: torch.Tensor, world_size: int, group) -> torch.Tensor:
-    """All-gather `[B_l, ...]` shards into one contiguous `[W*B_l, ...]` buffer (no list + cat copy)."""
+def _gather_rows_async(x: torch.Tensor, world_size: int, group):
+    """Start an all-gather of `[B_l, ...]` shards into one contiguous `[W*B_l, ...]` buffer (no list + cat copy).
+    Returns (buffer, work); `work.wait()` makes the current stream wait for the collective."""
     out = torch.empty((world_size * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
     try:
-        dist.all_gather_into_tensor(out, x.contiguous(), group=group)
+        work = dist.all_gather_into_tensor(out, x.contiguous(), group=group, async_op=True)
     except (RuntimeError, NotImplementedError):  # backends without the flat variant
-        dist.all_gather(list(out.chunk(world_size, dim=0)), x.contiguous(), group=group)
+        work = dist.all_gather(list(out.chunk(world_size, dim=0)), x.contiguous(), group=group, async_op=True)
+    return out, work
+
+
+def _gather_rows(x: torch.Tensor, world_size: int, group) -> torch.Tensor:
+    out, work = _gather_rows_async(x, world_size, group)
+    work.wait()
     return out
 
 
@@ -63,14 +70,23 @@ class ClipLossFunction(torch.autograd.Function):
         W = int(world_size)
         Bl = xi.shape[0]
         if W > 1:
-            all_i = _gather_rows(xi, W, group)
-            all_t = _gather_rows(xt, W, group)
+            # both gathers are in flight at once; the image gather overlaps the first kernel
+            all_t, work_t = _gather_rows_async(xt, W, group)
+            all_i, work_i = _gather_rows_async(xi, W, group)
             off = int(rank) * Bl
+            work_t.wait()
         else:
             all_i, all_t, off = xi, xt, 0
+            work_i = None
 
-        row_lse, diag = be.row_lse(xi, all_t, ls, off, True)     # rows R of S
-        col_lse, _ = be.row_lse(xt, all_i, ls, off, False)       # columns R of S
+        # u, v: softmax-weighted raw dots (sum_j P_ij <x_i, y_j>) of the two blocks -- all d(logit_scale) needs
+        need_ls = torch.is_tensor(logit_scale) and logit_scale.requires_grad
+        r1 = be.row_lse(xi, all_t, ls, off, True, need_ls)       # rows R of S
+        if work_i is not None:
+            work_i.wait()
+        r2 = be.row_lse(xt, all_i, ls, off, False, need_ls)      # columns R of S
+        row_lse, diag, col_lse = r1[0], r1[1], r2[0]
+        ctx.uv = (r1[2], r2[2]) if need_ls else None
         loss = be.loss_finalize(row_lse, col_lse, diag, ls)      # the rank's local loss
         if W > 1 and not local_loss:
             # reference: one global [B_g, B_g] problem on every rank == mean of the equal-sized rank losses
@@ -78,18 +94,16 @@ class ClipLossFunction(torch.autograd.Function):
             loss = loss / W
 
         own_terms_only = W > 1 and local_loss and not gather_with_grad
+        ctx.stats_work = None
         if W > 1 and not own_terms_only:
-            stats = _gather_rows(torch.stack((row_lse, col_lse)).unsqueeze(0), W, group)  # [W, 2, B_l]
-            row_lse_all = stats[:, 0, :].reshape(-1).contiguous()
-            col_lse_all = stats[:, 1, :].reshape(-1).contiguous()
-        elif own_terms_only:
-            row_lse_all = col_lse_all = None
+            # the LSE vectors of the other ranks are only needed by backward: start the gather now, wait there
+            stats, ctx.stats_work = _gather_rows_async(torch.stack((row_lse, col_lse)).unsqueeze(0), W, group)  # [W, 2, B_l]
         else:
-            row_lse_all, col_lse_all = row_lse, col_lse
+            stats = torch.stack((row_lse, col_lse)).unsqueeze(0)
 
-        ctx.save_for_backward(xi, xt, all_i, all_t, ls, row_lse, col_lse, diag,
-                              row_lse_all if row_lse_all is not None else row_lse,
-                              col_lse_all if col_lse_all is not None else col_lse)
+        # `stats` is written by the in-flight collective, so it is kept off autograd's version tracking
+        ctx.stats = stats
+        ctx.save_for_backward(xi, xt, all_i, all_t, ls, row_lse, col_lse, diag)
         ctx.cfg = (bool(local_loss), bool(gather_with_grad), W, off, own_terms_only, group)
         ctx.in_dtypes = (image_features.dtype, text_features.dtype)
         ctx.ls_meta = (logit_scale.dtype, logit_scale.shape, logit_scale.device) if torch.is_tensor(logit_scale) else None
@@ -98,8 +112,14 @@ class ClipLossFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         be = _cabi.get_backend()
-        xi, xt, all_i, all_t, ls, row_lse, col_lse, diag, row_lse_all, col_lse_all = ctx.saved_tensors
+        xi, xt, all_i, all_t, ls, row_lse, col_lse, diag = ctx.saved_tensors
+        stats = ctx.stats
         local_loss, gather_with_grad, W, off, own_terms_only, group = ctx.cfg
+        if ctx.stats_work is not None:
+            ctx.stats_work.wait()
+            ctx.stats_work = None
+        row_lse_all = stats[:, 0, :].reshape(-1)
+        col_lse_all = stats[:, 1, :].reshape(-1)
         Bl = xi.shape[0]
         Bg = W * Bl
         go = grad_out.detach().to(device=xi.device, dtype=torch.float32).reshape(1).contiguous()
@@ -117,12 +137,12 @@ class ClipLossFunction(torch.autograd.Function):
 
         need_i, need_t, need_ls = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         d_img = d_txt = d_ls = None
-        u = v = None
-        if need_i or need_ls:
-            d_img, u = be.block_grad(xi, all_t, ls, go, row_lse, lse_y_i, off, w_row, w_col, w_diag, inv_2n)
-        if need_t or need_ls:
-            d_txt, v = be.block_grad(xt, all_i, ls, go, col_lse, lse_y_t, off, w_row, w_col, w_diag, inv_2n)
-        if need_ls and ctx.ls_meta is not None:
+        if need_i:
+            d_img, _ = be.block_grad(xi, all_t, ls, go, row_lse, lse_y_i, off, w_row, w_col, w_diag, inv_2n, False)
+        if need_t:
+            d_txt, _ = be.block_grad(xt, all_i, ls, go, col_lse, lse_y_t, off, w_row, w_col, w_diag, inv_2n, False)
+        if need_ls and ctx.ls_meta is not None and ctx.uv is not None:
+            u, v = ctx.uv
             n_ls = Bl if (W > 1 and local_loss) else Bg
             t, d_ls = be.dls_finalize(u, v, diag, go, 1.0 / (2.0 * n_ls))
             if W > 1 and not local_loss:

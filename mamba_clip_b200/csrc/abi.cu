@@ -90,8 +90,8 @@ int mclip_workspace_bytes(int64_t M, int64_t N, int64_t D, int dtype, int op, in
 }
 
 int mclip_row_lse(const void* X, const void* Y, int64_t M, int64_t N, int64_t D, int64_t ldx, int64_t ldy,
-                  int dtype, const float* logit_scale, int64_t diag_off, float* lse, float* diag, void* ws,
-                  size_t ws_bytes, int path, void* cuda_stream) {
+                  int dtype, const float* logit_scale, int64_t diag_off, float* lse, float* diag, float* rowdot,
+                  void* ws, size_t ws_bytes, int path, void* cuda_stream) {
   int rc = check_common(X, Y, M, N, D, ldx, ldy, dtype, logit_scale, path, "row_lse");
   if (rc) return rc;
   if (!lse) { set_error("row_lse: lse is null"); return MCLIP_ERR_INVALID; }
@@ -100,7 +100,7 @@ int mclip_row_lse(const void* X, const void* Y, int64_t M, int64_t N, int64_t D,
   if (rc) return rc;
   const size_t need = (p == MCLIP_PATH_TCGEN05) ? tc_row_lse_ws(M, N, D) : simt_row_lse_ws(M, N, D);
   if (need > 0 && (!ws || ws_bytes < need)) { set_error("row_lse: workspace %zu < %zu bytes", ws_bytes, need); return MCLIP_ERR_WORKSPACE; }
-  RowLseArgs a{X, Y, M, N, D, ldx, ldy, dtype, logit_scale, diag_off, lse, diag, ws, ws_bytes, (cudaStream_t)cuda_stream};
+  RowLseArgs a{X, Y, M, N, D, ldx, ldy, dtype, logit_scale, diag_off, lse, diag, rowdot, ws, ws_bytes, (cudaStream_t)cuda_stream};
   return (p == MCLIP_PATH_TCGEN05) ? tc_row_lse(a) : simt_row_lse(a);
 }
 

@@ -37,6 +37,7 @@ struct RowLseArgs {
   int64_t diag_off;
   float* lse;
   float* diag;       // may be null
+  float* rowdot;     // may be null
   void* ws; size_t ws_bytes;
   cudaStream_t stream;
 };
@@ -71,9 +72,9 @@ size_t tc_block_grad_ws(int64_t M, int64_t N, int64_t D);
 int tc_block_grad(const BlockGradArgs& a);
 
 // shared small kernels -- simt_kernels.cu
-// merge `nsplit` partial (max2, sum) pairs per row into a natural-log LSE.
-int launch_lse_merge(const float* part_m2, const float* part_s, int nsplit, int64_t M, float* lse,
-                     cudaStream_t stream);
+// merge `nsplit` partial (max2, sum, sum*c) triples per row into a natural-log LSE (+ rowdot if asked for).
+int launch_lse_merge(const float* part_m2, const float* part_s, const float* part_c, int nsplit, int64_t M, float* lse,
+                     float* rowdot, cudaStream_t stream);
 int launch_loss_finalize(const float* row_lse, const float* col_lse, const float* diag, int64_t n,
                          const float* logit_scale, float* loss, cudaStream_t stream);
 int launch_dls_finalize(const float* u, const float* v, const float* diag, int64_t n, const float* grad_out,

@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(256)
 simt_row_lse_kernel(const T* __restrict__ X, const T* __restrict__ Y, int64_t M, int64_t N, int64_t D,
                     int64_t ldx, int64_t ldy, const float* __restrict__ ls_ptr, int64_t diag_off,
                     int64_t cols_per_split, float* __restrict__ part_m2, float* __restrict__ part_s,
-                    float* __restrict__ diag) {
+                    float* __restrict__ part_c, float* __restrict__ diag) {
   __shared__ float Xs[kBK][kFwdBM + 1];
   __shared__ float Ys[kBK][kFwdBN + 1];
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
@@ -40,9 +40,9 @@ simt_row_lse_kernel(const T* __restrict__ X, const T* __restrict__ Y, int64_t M,
   const int64_t c_end = min(N, c_begin + cols_per_split);
   const float k2 = ls_ptr[0] * kLog2e;
 
-  float m2[4], sum[4];
+  float m2[4], sum[4], sc[4];   // running max (log2 units), sum of 2^(x-m), sum of 2^(x-m) * <x_i,y_j>
 #pragma unroll
-  for (int a = 0; a < 4; ++a) { m2[a] = -INFINITY; sum[a] = 0.f; }
+  for (int a = 0; a < 4; ++a) { m2[a] = -INFINITY; sum[a] = 0.f; sc[a] = 0.f; }
 
   for (int64_t col0 = c_begin; col0 < c_end; col0 += kFwdBN) {
     float acc[4][4];
@@ -90,11 +90,16 @@ simt_row_lse_kernel(const T* __restrict__ X, const T* __restrict__ Y, int64_t M,
       tmax = warp16_max(tmax);
       const float m_new = fmaxf(m2[a], tmax);
       if (m_new > -INFINITY) {
-        float s = sum[a] * exp2f(m2[a] - m_new);  // m2 == -inf -> 0 * 0 = 0 (sum starts at 0)
-        if (m2[a] == -INFINITY) s = 0.f;
+        const float rescale = (m2[a] == -INFINITY) ? 0.f : exp2f(m2[a] - m_new);
+        float s = sum[a] * rescale, c = sc[a] * rescale;
 #pragma unroll
-        for (int b = 0; b < 4; ++b) s += exp2f(x[b] - m_new);
+        for (int b = 0; b < 4; ++b) {
+          const float e = exp2f(x[b] - m_new);     // 0 for masked columns (x = -inf)
+          s += e;
+          c = fmaf(e, acc[a][b], c);
+        }
         sum[a] = s;
+        sc[a] = c;
         m2[a] = m_new;
       }
     }
@@ -103,10 +108,12 @@ simt_row_lse_kernel(const T* __restrict__ X, const T* __restrict__ Y, int64_t M,
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
     const float s = warp16_sum(sum[a]);
+    const float c = warp16_sum(sc[a]);
     const int64_t row = row0 + ty * 4 + a;
     if (tx == 0 && row < M) {
       part_m2[(int64_t)blockIdx.y * M + row] = m2[a];
       part_s[(int64_t)blockIdx.y * M + row] = s;
+      part_c[(int64_t)blockIdx.y * M + row] = c;
     }
   }
 }
@@ -115,17 +122,23 @@ simt_row_lse_kernel(const T* __restrict__ X, const T* __restrict__ Y, int64_t M,
 // merge per-split partials:  lse = ln2 * (m + log2(sum_k s_k 2^(m_k - m)))
 // ---------------------------------------------------------------------------------------------
 __global__ void lse_merge_kernel(const float* __restrict__ part_m2, const float* __restrict__ part_s,
-                                 int nsplit, int64_t M, float* __restrict__ lse) {
+                                 const float* __restrict__ part_c, int nsplit, int64_t M, float* __restrict__ lse,
+                                 float* __restrict__ rowdot) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M) return;
   float m = -INFINITY;
   for (int k = 0; k < nsplit; ++k) m = fmaxf(m, part_m2[(int64_t)k * M + i]);
-  float s = 0.f;
+  float s = 0.f, c = 0.f;
   for (int k = 0; k < nsplit; ++k) {
     const float mk = part_m2[(int64_t)k * M + i];
-    if (mk > -INFINITY) s += part_s[(int64_t)k * M + i] * exp2f(mk - m);
+    if (mk > -INFINITY) {
+      const float w = exp2f(mk - m);
+      s += part_s[(int64_t)k * M + i] * w;
+      if (rowdot != nullptr) c += part_c[(int64_t)k * M + i] * w;
+    }
   }
   lse[i] = (m + log2f(s)) * kLn2;
+  if (rowdot != nullptr) rowdot[i] = c / s;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -295,7 +308,8 @@ int run_row_lse(const RowLseArgs& a) {
   const int real_splits = (int)ceil_div(a.N, cols_per_split);
   float* part_m2 = reinterpret_cast<float*>(a.ws);
   float* part_s = part_m2 + (size_t)real_splits * a.M;
-  if ((size_t)real_splits * a.M * 2 * sizeof(float) > a.ws_bytes) {
+  float* part_c = part_s + (size_t)real_splits * a.M;
+  if ((size_t)real_splits * a.M * 3 * sizeof(float) > a.ws_bytes) {
     set_error("row_lse(simt): workspace too small");
     return MCLIP_ERR_WORKSPACE;
   }
@@ -303,10 +317,10 @@ int run_row_lse(const RowLseArgs& a) {
   dim3 grid((unsigned)row_tiles, (unsigned)real_splits);
   simt_row_lse_kernel<T><<<grid, 256, 0, a.stream>>>(
       reinterpret_cast<const T*>(a.X), reinterpret_cast<const T*>(a.Y), a.M, a.N, a.D, a.ldx, a.ldy,
-      a.logit_scale, a.diag_off, cols_per_split, part_m2, part_s, a.diag);
+      a.logit_scale, a.diag_off, cols_per_split, part_m2, part_s, part_c, a.diag);
   count_launch();
   MCLIP_CUDA_OK(cudaGetLastError());
-  return launch_lse_merge(part_m2, part_s, real_splits, a.M, a.lse, a.stream);
+  return launch_lse_merge(part_m2, part_s, part_c, real_splits, a.M, a.lse, a.rowdot, a.stream);
 }
 
 template <typename T>
@@ -325,7 +339,7 @@ int run_block_grad(const BlockGradArgs& a) {
 
 size_t simt_row_lse_ws(int64_t M, int64_t N, int64_t) {
   const int nsplit = pick_splits(ceil_div(M, kFwdBM), ceil_div(N, kFwdBN));
-  return align_up((size_t)nsplit * M * 2 * sizeof(float), 256);
+  return align_up((size_t)nsplit * M * 3 * sizeof(float), 256);
 }
 size_t simt_block_grad_ws(int64_t, int64_t, int64_t) { return 0; }
 
@@ -349,9 +363,9 @@ int simt_block_grad(const BlockGradArgs& a) {
   return MCLIP_ERR_INVALID;
 }
 
-int launch_lse_merge(const float* part_m2, const float* part_s, int nsplit, int64_t M, float* lse,
-                     cudaStream_t stream) {
-  lse_merge_kernel<<<(unsigned)ceil_div(M, 256), 256, 0, stream>>>(part_m2, part_s, nsplit, M, lse);
+int launch_lse_merge(const float* part_m2, const float* part_s, const float* part_c, int nsplit, int64_t M, float* lse,
+                     float* rowdot, cudaStream_t stream) {
+  lse_merge_kernel<<<(unsigned)ceil_div(M, 256), 256, 0, stream>>>(part_m2, part_s, part_c, nsplit, M, lse, rowdot);
   count_launch();
   MCLIP_CUDA_OK(cudaGetLastError());
   return MCLIP_OK;

@@ -42,6 +42,7 @@ struct FwdParams {
   const float* ls;
   float* part_m2;
   float* part_s;
+  float* part_c;      // sum of 2^(x-m) * <x_i, y_j> per split (null: not wanted)
   float* diag;
   int bf16;
   int dbg;            // development switch (MCLIP_DBG & 16): print barrier-wait cycle counts of a few CTAs
@@ -72,9 +73,9 @@ __device__ __forceinline__ uint32_t align1024(uint32_t a) { return (a + 1023u) &
 // =================================================================================================
 // forward
 // =================================================================================================
-template <bool kMasked>
+template <bool kMasked, bool kDot>
 __device__ __forceinline__ void fwd_chunk(const uint32_t (&v)[32], float k2, int64_t col0, int64_t N, int64_t jd,
-                                          float& m2, float& sum, float& diag_val) {
+                                          float& m2, float& sum, float& sc, float& diag_val) {
   float x[32];
   float cmax = -INFINITY;
 #pragma unroll
@@ -90,10 +91,17 @@ __device__ __forceinline__ void fwd_chunk(const uint32_t (&v)[32], float k2, int
   }
   const float m_new = fmaxf(m2, cmax);
   if (m_new == -INFINITY) return;  // nothing valid yet (only possible in masked tail chunks)
-  float s = sum * ex2_approx(m2 - m_new);
+  const float rescale = ex2_approx(m2 - m_new);
+  float s = sum * rescale;
+  float c = kDot ? sc * rescale : 0.f;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) s += ex2_approx(x[j] - m_new);
+  for (int j = 0; j < 32; ++j) {
+    const float e = ex2_approx(x[j] - m_new);
+    s += e;
+    if (kDot) c = fmaf(e, __uint_as_float(v[j]), c);
+  }
   sum = s;
+  if (kDot) sc = c;
   m2 = m_new;
 }
 
@@ -111,6 +119,7 @@ tc_row_lse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   // misc layout: [0,1024) merge scratch (float2 x 128), then barriers
   uint8_t* misc_gen = smem_gen + (misc_base - smem_base);
   float2* merge = reinterpret_cast<float2*>(misc_gen);
+  float* merge_c = reinterpret_cast<float*>(misc_gen + 1536);   // [128]
   const uint32_t bar_base = misc_base + 1024;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
@@ -165,8 +174,9 @@ tc_row_lse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------- MMA issuer ----------------
+    {
+      // ---------------- MMA issuer: the whole warp waits, one elected lane issues ----------------
+      const bool elected = elect_one();
       const uint32_t idesc = make_idesc_f16(p.bf16 != 0, p.bf16 != 0, 128, BN, false, false);
       if (XRES) mbar_wait(xfull_bar, 0);
       uint32_t it = 0;
@@ -183,15 +193,18 @@ tc_row_lse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           tc_fence_after();
           const uint32_t b_addr = ring_base + s * kStageBytes;
           const uint32_t a_addr = XRES ? (smem_base + c * kChunkBytes) : (b_addr + kYStage);
+          if (elected) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t ad = make_smem_desc_sw128(a_addr + k * 32, 0, 1024);
-            const uint64_t bd = make_smem_desc_sw128(b_addr + k * 32, 0, 1024);
-            mma_ss(d_tmem, ad, bd, idesc, (c | k) != 0);
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t ad = make_smem_desc_sw128(a_addr + k * 32, 0, 1024);
+              const uint64_t bd = make_smem_desc_sw128(b_addr + k * 32, 0, 1024);
+              mma_ss(d_tmem, ad, bd, idesc, (c | k) != 0);
+            }
+            mma_commit(empty_bar(s));
+            if (c == p.kch - 1) mma_commit(tfull_bar(buf));
           }
-          mma_commit(empty_bar(s));
+          __syncwarp();
         }
-        mma_commit(tfull_bar(buf));
       }
     }
   } else if (warp >= kEpiWarp0) {
@@ -203,7 +216,8 @@ tc_row_lse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const int64_t row = m0 + row_in_tile;
     const float k2 = p.ls[0] * kLog2e;
     const int64_t jd = row + p.diag_off;  // this row's positive column
-    float m2 = -INFINITY, sum = 0.f, diag_val = 0.f;
+    float m2 = -INFINITY, sum = 0.f, sc = 0.f, diag_val = 0.f;
+    const bool want_dot = p.part_c != nullptr;
     constexpr int kHalfCols = BN / 2;
     for (int lt = 0; lt < ntiles; ++lt) {
       const int buf = lt & 1;
@@ -221,9 +235,13 @@ tc_row_lse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         tmem_ld_wait();
         const int64_t col0 = n0 + half * kHalfCols + cc * 32;
         if (special) {
-          if (col0 < p.N) fwd_chunk<true>(v, k2, col0, p.N, jd, m2, sum, diag_val);
+          if (col0 < p.N) {
+            if (want_dot) fwd_chunk<true, true>(v, k2, col0, p.N, jd, m2, sum, sc, diag_val);
+            else fwd_chunk<true, false>(v, k2, col0, p.N, jd, m2, sum, sc, diag_val);
+          }
         } else {
-          fwd_chunk<false>(v, k2, col0, p.N, jd, m2, sum, diag_val);
+          if (want_dot) fwd_chunk<false, true>(v, k2, col0, p.N, jd, m2, sum, sc, diag_val);
+          else fwd_chunk<false, false>(v, k2, col0, p.N, jd, m2, sum, sc, diag_val);
         }
       }
       tc_fence_before();
@@ -231,17 +249,18 @@ tc_row_lse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       if (lane == 0) mbar_arrive(tempty_bar(buf));
     }
     // merge the two column halves, then write the split's partial
-    if (half == 1) merge[row_in_tile] = make_float2(m2, sum);
+    if (half == 1) { merge[row_in_tile] = make_float2(m2, sum); merge_c[row_in_tile] = sc; }
     named_bar_sync(1, kEpiThreads);
     if (half == 0) {
       const float2 o = merge[row_in_tile];
       const float mm = fmaxf(m2, o.x);
-      float s = 0.f;
-      if (m2 > -INFINITY) s += sum * exp2f(m2 - mm);
-      if (o.x > -INFINITY) s += o.y * exp2f(o.x - mm);
+      float s = 0.f, c = 0.f;
+      if (m2 > -INFINITY) { const float w = exp2f(m2 - mm); s += sum * w; c += sc * w; }
+      if (o.x > -INFINITY) { const float w = exp2f(o.x - mm); s += o.y * w; c += merge_c[row_in_tile] * w; }
       if (row < p.M) {
         p.part_m2[(int64_t)blockIdx.y * p.M + row] = mm;
         p.part_s[(int64_t)blockIdx.y * p.M + row] = s;
+        if (want_dot) p.part_c[(int64_t)blockIdx.y * p.M + row] = c;
       }
     }
     if (p.diag != nullptr && row < p.M && jd >= 0 && jd < p.N) {
@@ -278,6 +297,7 @@ tc_row_lse2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   const uint32_t misc_base = ring_base + kFwd2Stages * kChunkBytes;
   uint8_t* misc_gen = smem_gen + (misc_base - smem_base);
   float2* merge = reinterpret_cast<float2*>(misc_gen);
+  float* merge_c = reinterpret_cast<float*>(misc_gen + 1536);   // [128]
   const uint32_t bar_base = misc_base + 1024;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };                 // leader
   auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };  // per CTA (multicast commit)
@@ -329,11 +349,12 @@ tc_row_lse2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && leader) {
+    if (leader) {
+      const bool elected = elect_one();
       const uint32_t idesc = make_idesc_f16(p.bf16 != 0, p.bf16 != 0, 256, BN, false, false);
       mbar_wait(xfull_bar, 0);
       uint32_t it = 0;
-      const bool prof = (p.dbg & 16) != 0;
+      const bool prof = (p.dbg & 16) != 0 && elected;
       long long t_full = 0, t_tempty = 0, t_begin = clock64();
       for (int lt = 0; lt < ntiles; ++lt) {
         const int buf = lt & 1;
@@ -356,15 +377,18 @@ tc_row_lse2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           tc_fence_after();
           const uint32_t b_addr = ring_base + s * kChunkBytes;
           const uint32_t a_addr = smem_base + c * kChunkBytes;
+          if (elected) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t ad = make_smem_desc_sw128(a_addr + k * 32, 0, 1024);
-            const uint64_t bd = make_smem_desc_sw128(b_addr + k * 32, 0, 1024);
-            mma_ss_cg2(d_tmem, ad, bd, idesc, (c | k) != 0);
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t ad = make_smem_desc_sw128(a_addr + k * 32, 0, 1024);
+              const uint64_t bd = make_smem_desc_sw128(b_addr + k * 32, 0, 1024);
+              mma_ss_cg2(d_tmem, ad, bd, idesc, (c | k) != 0);
+            }
+            mma_commit_cg2(empty_bar(s), 3);
+            if (c == p.kch - 1) mma_commit_cg2(tfull_bar(buf), 3);
           }
-          mma_commit_cg2(empty_bar(s), 3);
+          __syncwarp();
         }
-        mma_commit_cg2(tfull_bar(buf), 3);
       }
       if (prof && blockIdx.x < 4 && blockIdx.y == 0)
         printf("[fwd mma cta %d] tiles=%d total=%lld clk wait_full=%lld wait_tempty=%lld (per tile: total %lld full %lld tempty %lld)\n",
@@ -379,7 +403,8 @@ tc_row_lse2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     const int64_t row = m0 + row_in_tile;
     const float k2 = p.ls[0] * kLog2e;
     const int64_t jd = row + p.diag_off;
-    float m2 = -INFINITY, sum = 0.f, diag_val = 0.f;
+    float m2 = -INFINITY, sum = 0.f, sc = 0.f, diag_val = 0.f;
+    const bool want_dot = p.part_c != nullptr;
     constexpr int kHalfCols = BN / 2;
     const bool eprof = (p.dbg & 16) != 0 && warp == kEpiWarp0 && lane == 0;
     long long e_wait = 0, e_begin = clock64();
@@ -402,9 +427,13 @@ tc_row_lse2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         tmem_ld_wait();
         const int64_t col0 = n0 + half * kHalfCols + cc * 32;
         if (special) {
-          if (col0 < p.N) fwd_chunk<true>(v, k2, col0, p.N, jd, m2, sum, diag_val);
+          if (col0 < p.N) {
+            if (want_dot) fwd_chunk<true, true>(v, k2, col0, p.N, jd, m2, sum, sc, diag_val);
+            else fwd_chunk<true, false>(v, k2, col0, p.N, jd, m2, sum, sc, diag_val);
+          }
         } else {
-          fwd_chunk<false>(v, k2, col0, p.N, jd, m2, sum, diag_val);
+          if (want_dot) fwd_chunk<false, true>(v, k2, col0, p.N, jd, m2, sum, sc, diag_val);
+          else fwd_chunk<false, false>(v, k2, col0, p.N, jd, m2, sum, sc, diag_val);
         }
       }
       tc_fence_before();
@@ -416,17 +445,18 @@ tc_row_lse2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     if (eprof && blockIdx.x < 4 && blockIdx.y == 0)
       printf("[fwd epi cta %d] total=%lld clk wait_tfull=%lld (per tile: total %lld wait %lld)\n", (int)blockIdx.x,
              clock64() - e_begin, e_wait, (clock64() - e_begin) / max(ntiles, 1), e_wait / max(ntiles, 1));
-    if (half == 1) merge[row_in_tile] = make_float2(m2, sum);
+    if (half == 1) { merge[row_in_tile] = make_float2(m2, sum); merge_c[row_in_tile] = sc; }
     named_bar_sync(1, kEpiThreads);
     if (half == 0) {
       const float2 o = merge[row_in_tile];
       const float mm = fmaxf(m2, o.x);
-      float s = 0.f;
-      if (m2 > -INFINITY) s += sum * exp2f(m2 - mm);
-      if (o.x > -INFINITY) s += o.y * exp2f(o.x - mm);
+      float s = 0.f, c = 0.f;
+      if (m2 > -INFINITY) { const float w = exp2f(m2 - mm); s += sum * w; c += sc * w; }
+      if (o.x > -INFINITY) { const float w = exp2f(o.x - mm); s += o.y * w; c += merge_c[row_in_tile] * w; }
       if (row < p.M) {
         p.part_m2[(int64_t)blockIdx.y * p.M + row] = mm;
         p.part_s[(int64_t)blockIdx.y * p.M + row] = s;
+        if (want_dot) p.part_c[(int64_t)blockIdx.y * p.M + row] = c;
       }
     }
     if (p.diag != nullptr && row < p.M && jd >= 0 && jd < p.N) {
@@ -561,8 +591,9 @@ tc_block_grad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------- MMA issuer ----------------
+    {
+      // ---------------- MMA issuer: the whole warp waits, one elected lane issues ----------------
+      const bool elected = elect_one();
       const uint32_t idesc_s = make_idesc_f16(kBF16, kBF16, 128, 128, false, false);
       // with kGF16 both dX operands are f16: G, and the f16 copy of Y behind tmY16
       const uint32_t idesc_dx = make_idesc_f16(kBF16 && !kGF16, kBF16 && !kGF16, 128, (uint32_t)ndc * 64, false, true);
@@ -581,15 +612,18 @@ tc_block_grad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           tc_fence_after();
           const uint32_t b_addr = ring_base + s * kStageBytes;
           const uint32_t a_addr = XRES ? (smem_base + c * kChunkBytes) : (b_addr + kChunkBytes);
+          if (elected) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t ad = make_smem_desc_sw128(a_addr + k * 32, 0, 1024);
-            const uint64_t bd = make_smem_desc_sw128(b_addr + k * 32, 0, 1024);
-            mma_ss(d_tmem, ad, bd, idesc_s, (c | k) != 0);
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t ad = make_smem_desc_sw128(a_addr + k * 32, 0, 1024);
+              const uint64_t bd = make_smem_desc_sw128(b_addr + k * 32, 0, 1024);
+              mma_ss(d_tmem, ad, bd, idesc_s, (c | k) != 0);
+            }
+            mma_commit(empty_bar(s));
+            if (c == p.kch - 1) mma_commit(sfull_bar(buf));
           }
-          mma_commit(empty_bar(s));
+          __syncwarp();
         }
-        mma_commit(sfull_bar(buf));
       };
       auto issue_dx = [&](int ls_) {
         const int buf = ls_ & 1;
@@ -597,23 +631,26 @@ tc_block_grad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         mbar_wait(gfull_bar(buf), bph);
         mbar_wait(ydfull_bar, ls_ & 1);
         tc_fence_after();
+        if (elected) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          // A = G[128 x 16] from TMEM (8 packed columns per k-step); B = Y[16 y][64*ndc d], MN-major:
-          // 64-wide d atoms are kChunkBytes apart (LBO), 8-row y groups 1024 B apart (SBO).
-          const uint32_t a_tmem = tmem_base + buf * 128 + (k < 4 ? k * 8 : 64 + (k - 4) * 8);
-          const uint64_t bd = make_smem_desc_sw128(yd_base + k * 2048, kChunkBytes, 1024);
-          mma_ts(tmem_base + kDxCol, a_tmem, bd, idesc_dx, (ls_ | k) != 0);
+          for (int k = 0; k < 8; ++k) {
+            // A = G[128 x 16] from TMEM (8 packed columns per k-step); B = Y[16 y][64*ndc d], MN-major:
+            // 64-wide d atoms are kChunkBytes apart (LBO), 8-row y groups 1024 B apart (SBO).
+            const uint32_t a_tmem = tmem_base + buf * 128 + (k < 4 ? k * 8 : 64 + (k - 4) * 8);
+            const uint64_t bd = make_smem_desc_sw128(yd_base + k * 2048, kChunkBytes, 1024);
+            mma_ts(tmem_base + kDxCol, a_tmem, bd, idesc_dx, (ls_ | k) != 0);
+          }
+          mma_commit(ydempty_bar);
+          mma_commit(sempty_bar(buf));
+          if (ls_ == nsteps - 1) mma_commit(dxfull_bar);
         }
-        mma_commit(ydempty_bar);
-        mma_commit(sempty_bar(buf));
+        __syncwarp();
       };
       if (nsteps > 0) issue_s(0);
       for (int ls_ = 0; ls_ < nsteps; ++ls_) {
         if (ls_ + 1 < nsteps) issue_s(ls_ + 1);
         issue_dx(ls_);
       }
-      mma_commit(dxfull_bar);
     }
   } else if (warp >= kEpiWarp0) {
     // ---------------- epilogue: S -> G (16-bit, back into TMEM), then dX out ----------------
@@ -813,6 +850,7 @@ struct Bwd2Params {
 constexpr uint32_t kTile8K = 64 * 64 * 2;     // [64 rows x 64 k]
 constexpr uint32_t kStage2 = 2 * kChunkBytes; // ring stage: two [128 x 64] tiles
 constexpr int kRing2 = 4;
+constexpr int kRing3 = 3;             // the transposed kernel double-buffers G instead
 constexpr float kGScale = 4096.f;             // G is stored as G * 2^12 in f16
 
 template <bool kMasked, bool kCol>
@@ -882,7 +920,13 @@ __device__ __forceinline__ void bwd2_chunk_fast(const uint32_t (&v)[32], uint32_
   }
 }
 
-template <bool kBF16, int kPairs>
+// kGT: G is handed to the dX MMA through TMEM (TS form) instead of shared memory.  With 64 rows per CTA an SS MMA
+// fetches A (2 KB) + B (4 KB) per 64 ideal cycles = 96 B/clk, above the ~64 B/clk the tensor core sustains from
+// shared memory (measured ~100 clk per MMA); the TS form only fetches B.  For cta_group::2 with M = 128 the A rows
+// must be present in both lane halves of each CTA's TMEM ("duplicated" layout), so the epilogue exchanges the two
+// column halves of a row through a swizzled shared-memory buffer and every thread overwrites exactly the S columns
+// it loaded with the packed f16 G values.
+template <bool kBF16, int kPairs, bool kGT>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
                       const __grid_constant__ CUtensorMap tmY16, const Bwd2Params p) {
@@ -902,8 +946,12 @@ tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   const uint32_t gfull_bar = bar_base + 8u * 11;                         // leader: 16 epilogue warps
   const uint32_t gempty_bar = bar_base + 8u * 13;                        // per CTA, multicast
   const uint32_t dxfull_bar = bar_base + 8u * 15;                        // per CTA, multicast
-  const uint32_t tmem_slot = bar_base + 8u * 16;
-  uint32_t* tmem_slot_gen = reinterpret_cast<uint32_t*>(misc_gen + 8u * 16);
+  auto sread_bar = [&](int b) { return bar_base + 8u * (17 + b); };     // leader: 16 epilogue warps have loaded S(b)
+  const uint32_t tmem_slot = bar_base + 8u * 19;
+  uint32_t* tmem_slot_gen = reinterpret_cast<uint32_t*>(misc_gen + 8u * 19);
+  // kDeep: the S MMAs run two steps ahead of the dX MMAs (S(st+2) is issued as soon as the epilogue has pulled S(st)
+  // out of TMEM), which gives the epilogue two S durations instead of one before dX(st) needs G(st).
+  constexpr bool kDeep = !kGT;
   float* rd_scratch = reinterpret_cast<float*>(misc_gen + 256);          // [4][64]
   float* range_scratch = reinterpret_cast<float*>(misc_gen + 1280);      // [8][2]
 
@@ -929,7 +977,7 @@ tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     tma_prefetch_desc(&tmY16);
     for (int s = 0; s < kRing2; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), kPairs); }
     mbar_init(xfull_bar, 2);
-    for (int b = 0; b < 2; ++b) mbar_init(sfull_bar(b), 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(sfull_bar(b), 1); mbar_init(sread_bar(b), 2 * (kEpiThreads / 32)); }
     mbar_init(gfull_bar, 2 * (kEpiThreads / 32));
     mbar_init(gempty_bar, 1);
     mbar_init(dxfull_bar, 1);
@@ -989,23 +1037,33 @@ tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
           }
         }
       };
-      if (nsteps > 0) load_s(0);
-      for (int st = 0; st < nsteps; ++st) {
-        if (st + 1 < nsteps) load_s(st + 1);
-        load_dx(st);
+      if (kDeep) {
+        if (nsteps > 0) load_s(0);
+        if (nsteps > 1) load_s(1);
+        for (int st = 0; st < nsteps; ++st) {
+          if (st + 2 < nsteps) load_s(st + 2);
+          load_dx(st);
+        }
+      } else {
+        if (nsteps > 0) load_s(0);
+        for (int st = 0; st < nsteps; ++st) {
+          if (st + 1 < nsteps) load_s(st + 1);
+          load_dx(st);
+        }
       }
       if (pprof && blockIdx.x < 4 && blockIdx.y == 0)
         printf("[tma cta %d] total=%lld clk  wait_empty=%lld (per step: total %lld empty %lld)\n", (int)blockIdx.x,
                clock64() - p_begin, p_empty, (clock64() - p_begin) / max(nsteps, 1), p_empty / max(nsteps, 1));
     }
   } else if (warp == 1) {
-    if (lane == 0 && leader) {
-      // ---------------- MMA issuer (leader CTA only) ----------------
+    if (leader) {
+      // ---------------- MMA issuer (leader CTA only): the whole warp waits, one elected lane issues ----------------
+      const bool elected = elect_one();
       const uint32_t idesc_s = make_idesc_f16(kBF16, kBF16, 128, 256, false, false);
       const uint32_t idesc_dx = make_idesc_f16(false, false, 128, 256, false, true);
       mbar_wait(xfull_bar, 0);
       uint32_t it = 0;
-      const bool prof = (p.dbg & 16) != 0;
+      const bool prof = (p.dbg & 16) != 0 && elected;
       long long t_full = 0, t_gfull = 0, t_begin = clock64();
       auto stage_wait = [&]() -> uint32_t {
         const int s = it % kRing2;
@@ -1025,18 +1083,21 @@ tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         for (int i = 0; i < p.kpairs; ++i) {
           const uint32_t s = stage_wait();
           const uint32_t b_addr = ring_base + s * kStage2;
+          if (elected) {
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
+            for (int e = 0; e < 2; ++e) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t ad = make_smem_desc_sw128(x_base + (2 * i + e) * kTile8K + k * 32, 0, 1024);
-              const uint64_t bd = make_smem_desc_sw128(b_addr + e * kChunkBytes + k * 32, 0, 1024);
-              if (!(p.dbg & 2)) mma_ss_cg2(d_tmem, ad, bd, idesc_s, (i | e | k) != 0);
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t ad = make_smem_desc_sw128(x_base + (2 * i + e) * kTile8K + k * 32, 0, 1024);
+                const uint64_t bd = make_smem_desc_sw128(b_addr + e * kChunkBytes + k * 32, 0, 1024);
+                if (!(p.dbg & 2)) mma_ss_cg2(d_tmem, ad, bd, idesc_s, (i | e | k) != 0);
+              }
             }
+            mma_commit_cg2(empty_bar(s), kAllMask);
+            if (i == p.kpairs - 1) mma_commit_cg2(sfull_bar(buf), pair_mask);
           }
-          mma_commit_cg2(empty_bar(s), kAllMask);
+          __syncwarp();
         }
-        mma_commit_cg2(sfull_bar(buf), pair_mask);
       };
       auto issue_dx = [&](int st) {
         {
@@ -1049,24 +1110,48 @@ tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
           for (int h = 0; h < p.ndh; ++h) {
             const uint32_t s = stage_wait();
             const uint32_t b_addr = ring_base + s * kStage2;
+            if (elected) {
 #pragma unroll
-            for (int kk = 0; kk < 8; ++kk) {
-              // A = G[64 rows x 16 y] of K-chunk (2*yh + kk/4); B = Y16[16 y][128 d per CTA], MN-major
-              const uint64_t ad = make_smem_desc_sw128(g_base + (2 * yh + (kk >> 2)) * kTile8K + (kk & 3) * 32, 0, 1024);
-              const uint64_t bd = make_smem_desc_sw128(b_addr + kk * 2048, kChunkBytes, 1024);
-              if (!(p.dbg & 4)) mma_ss_cg2(tmem_base + kDxCol + h * 128, ad, bd, idesc_dx, (st | yh | kk) != 0);
+              for (int kk = 0; kk < 8; ++kk) {
+                // A = G[64 rows x 16 y] of K-chunk (2*yh + kk/4); B = Y16[16 y][128 d per CTA], MN-major
+                const uint64_t bd = make_smem_desc_sw128(b_addr + kk * 2048, kChunkBytes, 1024);
+                if (kGT) {
+                  // G(st) sits in the S buffer of this step: 8 packed columns per 16 y
+                  const uint32_t a_tmem = tmem_base + (st & 1) * 128 + (yh * 8 + kk) * 8;
+                  if (!(p.dbg & 4)) mma_ts_cg2(tmem_base + kDxCol + h * 128, a_tmem, bd, idesc_dx, (st | yh | kk) != 0);
+                } else {
+                  const uint64_t ad = make_smem_desc_sw128(g_base + (2 * yh + (kk >> 2)) * kTile8K + (kk & 3) * 32, 0, 1024);
+                  if (!(p.dbg & 4)) mma_ss_cg2(tmem_base + kDxCol + h * 128, ad, bd, idesc_dx, (st | yh | kk) != 0);
+                }
+              }
+              mma_commit_cg2(empty_bar(s), kAllMask);
+              if (yh == 1 && h == p.ndh - 1) {
+                mma_commit_cg2(gempty_bar, pair_mask);
+                if (st == nsteps - 1) mma_commit_cg2(dxfull_bar, pair_mask);
+              }
             }
-            mma_commit_cg2(empty_bar(s), kAllMask);
+            __syncwarp();
           }
         }
-        mma_commit_cg2(gempty_bar, pair_mask);
       };
-      if (nsteps > 0) issue_s(0);
-      for (int st = 0; st < nsteps; ++st) {
-        if (st + 1 < nsteps) issue_s(st + 1);
-        issue_dx(st);
+      if (kDeep) {
+        if (nsteps > 0) issue_s(0);
+        if (nsteps > 1) issue_s(1);
+        for (int st = 0; st < nsteps; ++st) {
+          if (st + 2 < nsteps) {
+            mbar_wait(sread_bar(st & 1), (st >> 1) & 1);   // S(st) is in registers: its TMEM buffer may be overwritten
+            tc_fence_after();
+            issue_s(st + 2);
+          }
+          issue_dx(st);
+        }
+      } else {
+        if (nsteps > 0) issue_s(0);
+        for (int st = 0; st < nsteps; ++st) {
+          if (st + 1 < nsteps) issue_s(st + 1);
+          issue_dx(st);
+        }
       }
-      mma_commit_cg2(dxfull_bar, pair_mask);
       if (prof && blockIdx.x < 4 && blockIdx.y == 0)
         printf("[mma cta %d] steps=%d total=%lld clk  wait_full=%lld  wait_gfull=%lld  (per step: total %lld full %lld gfull %lld)\n",
                (int)blockIdx.x, nsteps, clock64() - t_begin, t_full, t_gfull, (clock64() - t_begin) / max(nsteps, 1),
@@ -1139,6 +1224,13 @@ tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         uint32_t v[32];
         tmem_ld32(lane_addr + buf * 128 + half * 64 + cc * 32, v);
         tmem_ld_wait();
+        if (kDeep && cc == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (leader) mbar_arrive(sread_bar(buf)); else mbar_arrive_cluster(sread_bar(buf), leader_rank);
+          }
+        }
         const int64_t col0 = n0 + cS + cc * 32;
         const float* ly2 = has_col ? p.ly2 + col0 : nullptr;
         if (p.dbg & 1) {
@@ -1155,6 +1247,37 @@ tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
           else bwd2_chunk<false, false>(v, g[cc], k2, lx2, ly2, w_diag_s, col0, p.N, jd, rd);
         }
       }
+      if (kGT) {
+        // exchange through shared memory: row r of the buffer is 256 f16 = 32 16-byte pieces, piece index XOR (r & 7)
+        const uint32_t x_row = g_base + r * 512;
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+#pragma unroll
+          for (int pc = 0; pc < 4; ++pc) {
+            const uint32_t piece = (uint32_t)((cS >> 3) + cc * 4 + pc) ^ (uint32_t)(r & 7);
+            st_shared_v4(x_row + piece * 16, g[cc][4 * pc], g[cc][4 * pc + 1], g[cc][4 * pc + 2], g[cc][4 * pc + 3]);
+          }
+        }
+        named_bar_sync(1, kEpiThreads);      // all halves of every row are in place (and all S loads are done)
+        // this thread stores y in [128*half, 128*half + 128) of row r = 64 packed columns, over the S columns it loaded
+#pragma unroll
+        for (int blk = 0; blk < 4; ++blk) {
+          uint32_t w[16];
+#pragma unroll
+          for (int pc = 0; pc < 4; ++pc) {
+            const uint32_t piece = (uint32_t)(half * 16 + blk * 4 + pc) ^ (uint32_t)(r & 7);
+            ld_shared_v4(x_row + piece * 16, w[4 * pc], w[4 * pc + 1], w[4 * pc + 2], w[4 * pc + 3]);
+          }
+          tmem_st16(lane_addr + buf * 128 + half * 64 + blk * 16, w);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        named_bar_sync(2, kEpiThreads);      // the exchange buffer may be rewritten
+        __syncwarp();
+        if (lane == 0) {
+          if (leader) mbar_arrive(gfull_bar); else mbar_arrive_cluster(gfull_bar, leader_rank);
+        }
+      } else {
       tc_fence_before();          // TMEM reads of S are complete
       // G is single-buffered: the dX MMAs of the previous step must have finished reading it.  The values are
       // already in registers, so this wait overlaps with the S MMAs of the next step on the tensor pipe.
@@ -1176,6 +1299,7 @@ tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       __syncwarp();
       if (lane == 0) {
         if (leader) mbar_arrive(gfull_bar); else mbar_arrive_cluster(gfull_bar, leader_rank);
+      }
       }
     }
     if (eprof && blockIdx.x < 4 && blockIdx.y == 0)
@@ -1325,6 +1449,435 @@ __global__ void bf16_to_f16_kernel(const __nv_bfloat16* __restrict__ src, int64_
       h[e] = __floats2half2_rn(f.x, f.y);
     }
     *reinterpret_cast<uint4*>(dst + r * D + c) = out;
+  }
+}
+
+// =================================================================================================
+// backward, transposed CTA-pair version (D <= 512): both MMAs math-bound
+// =================================================================================================
+// Measured on B200: a tcgen05.mma fetches its B operand from shared memory at ~42 B/clk, so an instruction is
+// B-bound unless M per CTA >= ~98 rows -- the pair kernel above (64 X rows per CTA, B = 128 Y rows) runs ~100 clk
+// per MMA instead of 64.  Here the roles are swapped so that the small operand is B:
+//   S^T  = Y X^T        M = 256 (y: 128 per CTA)  N = 128 (x: 64 per CTA, resident)   -> [128 y x 128 x] per CTA
+//   dX^T += Y16^T G^T   M = 256 (d: 128 per CTA, MN-major A)  N = 128 (x)  K = 256 (y) -> [128 d x 128 x] x 2 halves of D
+// TMEM use is unchanged (2 x 128 + 256 columns).  The epilogue holds y on lanes, so a thread produces one row
+// G^T[y, 64 x] = one 128-byte line of the B operand [K = y][N = x].  The K dimension (y) of dX^T spans both CTAs,
+// while the N split gives CTA r the x half r: the warpgroup whose x half belongs to the peer writes its lines
+// straight into the peer's shared memory (st.shared::cluster) -- 16 KB per step and CTA.
+struct Bwd3Params {
+  int64_t M, N, D;
+  int kpairs, ndh, steps_total, steps_per_split, nsplit;
+  int64_t diag_off;
+  const float* ls;
+  const float* go;
+  const float* lx2;     // [m_pad] lse_x in log2 units, row weight and G scale folded, +inf padded
+  const float* bx;      // [m_pad] 2^(mu0 - lx2[x]) (0 in the padding)
+  const float* xmm;     // [m_pad / 128][2] min / max of lx2 per 128-row block
+  const float* ly2;     // [n_pad] lse_y in log2 units, column weight and G scale folded, +inf padded (null: no column term)
+  const float* ymm;     // [n_pad / 128][2]
+  const float* mu0;     // [1]
+  float w_diag, inv_2n;
+  int has_col;
+  void* dX;
+  int64_t lddx;
+  float* acc_ws;
+  int dbg;
+};
+
+// mode: 0 = one exponential (P^col and the separable factor), 1 = two exponentials, 2 = row term only
+template <int kMode, bool kMasked>
+__device__ __forceinline__ void bwd3_chunk(const uint32_t (&v)[32], uint32_t (&g)[16], float k2, float ly, float a_y,
+                                           const float* __restrict__ xarr, float w_diag_s, int xd, bool y_ok) {
+  float xa[32];   // kMode 0: b_x, else lx2[x]
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(xarr + j));
+    xa[j] = t.x; xa[j + 1] = t.y; xa[j + 2] = t.z; xa[j + 3] = t.w;
+  }
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    float gv[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const float c = __uint_as_float(v[j + e]);
+      float gg;
+      if (kMode == 0) gg = ex2_approx(fmaf(c, k2, -ly)) * fmaf(a_y, xa[j + e], 1.f);
+      else if (kMode == 1) gg = ex2_approx(fmaf(c, k2, -ly)) + ex2_approx(fmaf(c, k2, -xa[j + e]));
+      else gg = ex2_approx(fmaf(c, k2, -xa[j + e]));
+      if (kMasked) {
+        if (j + e == xd) gg -= w_diag_s;
+        if (!y_ok) gg = 0.f;
+      }
+      gv[e] = gg;
+    }
+    g[j >> 1] = pack_f16x2(gv[0], gv[1]);
+  }
+}
+
+template <bool kBF16>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_block_grad3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
+                      const __grid_constant__ CUtensorMap tmY16, const Bwd3Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = align1024(smem_u32(smem_raw));
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t x_base = smem_base;                              // [8][64 x rows][64 k]          64 KB
+  const uint32_t g_base = x_base + 8 * kTile8K;                   // [2][256 y][64 x] f16, MN-major 64 KB (double buffer)
+  const uint32_t ring_base = g_base + 8 * kTile8K;                // [kRing3][2][128][64]           96 KB
+  const uint32_t misc_base = ring_base + kRing3 * kStage2;
+  uint8_t* misc_gen = smem_gen + (misc_base - smem_base);
+  const uint32_t bar_base = misc_base;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };             // leader: both CTAs' TMA bytes
+  auto empty_bar = [&](int s) { return bar_base + 8u * (4 + s); };      // per CTA, MMA commit multicast
+  const uint32_t xfull_bar = bar_base + 8u * 8;                          // leader
+  auto sfull_bar = [&](int b) { return bar_base + 8u * (9 + b); };      // per CTA, multicast
+  auto gfull_bar = [&](int b) { return bar_base + 8u * (11 + b); };     // leader: 16 epilogue warps
+  auto gempty_bar = [&](int b) { return bar_base + 8u * (13 + b); };    // per CTA, multicast
+  const uint32_t dxfull_bar = bar_base + 8u * 15;                        // per CTA, multicast
+  const uint32_t tmem_slot = bar_base + 8u * 16;
+  uint32_t* tmem_slot_gen = reinterpret_cast<uint32_t*>(misc_gen + 8u * 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int64_t pair_row0 = (int64_t)(blockIdx.x >> 1) * 128;        // the pair's 128 x rows
+  const int s0 = blockIdx.y * p.steps_per_split;
+  const int s1 = min(p.steps_total, s0 + p.steps_per_split);
+  const int nsteps = s1 - s0;
+  constexpr uint32_t kTmemCols = 512;
+  constexpr uint32_t kDxCol = 256;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmY);
+    tma_prefetch_desc(&tmY16);
+    for (int s = 0; s < kRing3; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
+    mbar_init(xfull_bar, 2);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(sfull_bar(b), 1);
+      mbar_init(gfull_bar(b), 2 * (kEpiThreads / 32));
+      mbar_init(gempty_bar(b), 1);
+    }
+    mbar_init(dxfull_bar, 1);
+    fence_barrier_init();
+  } else if (warp == 2) {
+    tmem_alloc_cg2(tmem_slot, kTmemCols);
+    tmem_relinquish_cg2();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer (both CTAs) ----------------
+      // X: this CTA's 64 rows of the pair's block (the N operand of S^T), all of D, resident
+      if (leader) mbar_expect_tx(xfull_bar, 2 * 8 * kTile8K); else mbar_arrive_cluster(xfull_bar, 0);
+      for (int c = 0; c < 8; ++c)
+        tma_load_2d_cg2(x_base + c * kTile8K, &tmX, c * 64, (int32_t)(pair_row0 + 64 * rank), xfull_bar);
+      uint32_t it = 0;
+      auto stage_begin = [&]() -> uint32_t {
+        const int s = it % kRing3;
+        const uint32_t ph = (it / kRing3) & 1;
+        mbar_wait(empty_bar(s), ph ^ 1);
+        if (leader) mbar_expect_tx(full_bar(s), 2 * kStage2); else mbar_arrive_cluster(full_bar(s), 0);
+        ++it;
+        return (uint32_t)s;
+      };
+      auto load_s = [&](int st) {   // Y rows of this CTA's half of the step (the M operand of S^T), all of D
+        const int32_t y0 = (s0 + st) * 256 + 128 * (int32_t)rank;
+        for (int i = 0; i < p.kpairs; ++i) {
+          const uint32_t s = stage_begin();
+          const uint32_t dst = ring_base + s * kStage2;
+          tma_load_2d_cg2(dst, &tmY, (2 * i) * 64, y0, full_bar(s));
+          tma_load_2d_cg2(dst + kChunkBytes, &tmY, (2 * i + 1) * 64, y0, full_bar(s));
+        }
+      };
+      auto load_dx = [&](int st) {  // Y16[y half][this CTA's 128 d of half h]: the MN-major M operand of dX^T
+        for (int yh = 0; yh < 2; ++yh) {
+          const int32_t y0 = (s0 + st) * 256 + 128 * yh;
+          for (int h = 0; h < p.ndh; ++h) {
+            const uint32_t s = stage_begin();
+            const uint32_t dst = ring_base + s * kStage2;
+            const int32_t dcol = (4 * h + 2 * (int32_t)rank) * 64;
+            tma_load_2d_cg2(dst, &tmY16, dcol, y0, full_bar(s));
+            tma_load_2d_cg2(dst + kChunkBytes, &tmY16, dcol + 64, y0, full_bar(s));
+          }
+        }
+      };
+      if (nsteps > 0) load_s(0);
+      for (int st = 0; st < nsteps; ++st) {
+        if (st + 1 < nsteps) load_s(st + 1);
+        load_dx(st);
+      }
+    }
+  } else if (warp == 1) {
+    if (leader) {
+      // ---------------- MMA issuer (leader CTA only): the whole warp waits, one elected lane issues ----------------
+      const bool elected = elect_one();
+      const uint32_t idesc_s = make_idesc_f16(kBF16, kBF16, 256, 128, false, false);
+      const uint32_t idesc_dx = make_idesc_f16(false, false, 256, 128, true, true);
+      mbar_wait(xfull_bar, 0);
+      uint32_t it = 0;
+      const bool prof = (p.dbg & 16) != 0 && elected;
+      long long t_full = 0, t_gfull = 0, t_begin = clock64();
+      auto stage_wait = [&]() -> uint32_t {
+        const int s = it % kRing3;
+        const uint32_t ph = (it / kRing3) & 1;
+        const long long t0 = prof ? clock64() : 0;
+        mbar_wait(full_bar(s), ph);
+        if (prof) t_full += clock64() - t0;
+        tc_fence_after();
+        ++it;
+        return (uint32_t)s;
+      };
+      auto issue_s = [&](int st) {
+        const uint32_t d_tmem = tmem_base + (st & 1) * 128;
+        for (int i = 0; i < p.kpairs; ++i) {
+          const uint32_t s = stage_wait();
+          const uint32_t a_addr = ring_base + s * kStage2;
+          if (elected) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t ad = make_smem_desc_sw128(a_addr + e * kChunkBytes + k * 32, 0, 1024);       // Y [128 y][64 k]
+                const uint64_t bd = make_smem_desc_sw128(x_base + (2 * i + e) * kTile8K + k * 32, 0, 1024);  // X [64 x][64 k]
+                mma_ss_cg2(d_tmem, ad, bd, idesc_s, (i | e | k) != 0);
+              }
+            }
+            mma_commit_cg2(empty_bar(s), 3);
+            if (i == p.kpairs - 1) mma_commit_cg2(sfull_bar(st & 1), 3);
+          }
+          __syncwarp();
+        }
+      };
+      auto issue_dx = [&](int st) {
+        {
+          const long long t0 = prof ? clock64() : 0;
+          mbar_wait_acquire_cluster(gfull_bar(st & 1), (st >> 1) & 1);
+          if (prof) t_gfull += clock64() - t0;
+        }
+        tc_fence_after();
+        for (int yh = 0; yh < 2; ++yh) {
+          for (int h = 0; h < p.ndh; ++h) {
+            const uint32_t s = stage_wait();
+            const uint32_t a_addr = ring_base + s * kStage2;
+            if (elected) {
+#pragma unroll
+              for (int kk = 0; kk < 8; ++kk) {
+                // A = Y16^T: [M = 128 d per CTA (two 64-wide atoms, kChunkBytes apart)][K = 16 y], MN-major
+                // B = G^T:   [N = 64 x per CTA (one atom)][K = 16 y], MN-major, rows (yh*8 + kk)*16 .. of the G tile
+                const uint64_t ad = make_smem_desc_sw128(a_addr + kk * 2048, kChunkBytes, 1024);
+                const uint64_t bd = make_smem_desc_sw128(g_base + (st & 1) * (4 * kTile8K) + (yh * 8 + kk) * 2048, 0, 1024);
+                mma_ss_cg2(tmem_base + kDxCol + h * 128, ad, bd, idesc_dx, (st | yh | kk) != 0);
+              }
+              mma_commit_cg2(empty_bar(s), 3);
+              if (yh == 1 && h == p.ndh - 1) {
+                mma_commit_cg2(gempty_bar(st & 1), 3);
+                if (st == nsteps - 1) mma_commit_cg2(dxfull_bar, 3);
+              }
+            }
+            __syncwarp();
+          }
+        }
+      };
+      if (nsteps > 0) issue_s(0);
+      for (int st = 0; st < nsteps; ++st) {
+        if (st + 1 < nsteps) issue_s(st + 1);
+        issue_dx(st);
+      }
+      if (prof && blockIdx.x < 2 && blockIdx.y == 0)
+        printf("[mma3 cta %d] steps=%d total=%lld clk wait_full=%lld wait_gfull=%lld (per step: total %lld full %lld gfull %lld)\n",
+               (int)blockIdx.x, nsteps, clock64() - t_begin, t_full, t_gfull, (clock64() - t_begin) / max(nsteps, 1),
+               t_full / max(nsteps, 1), t_gfull / max(nsteps, 1));
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ---------------- epilogue: S^T -> G^T rows (f16 * 2^12) into the owner's G tile; finally dX^T out ----------------
+    const int ew = warp - kEpiWarp0;
+    const int q = warp & 3;                   // TMEM lane quadrant
+    const int half = ew >> 2;                 // x half handled by this warpgroup = CTA that consumes it as B operand
+    const int yl = q * 32 + lane;             // y row within this CTA's 128 (TMEM lane)
+    const float ls = p.ls[0];
+    const float k2 = ls * kLog2e;
+    const bool has_col = p.has_col != 0;
+    const float w_diag_s = p.w_diag * kGScale;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int64_t xg0 = pair_row0 + half * 64;             // first global x of this thread's columns
+    // destination of this thread's G line: row (128 * rank + yl) of the G tile in CTA `half`
+    const uint32_t grow = (uint32_t)(128 * rank + yl);
+    const uint32_t g_line_local = g_base + grow * 128;
+    const bool remote = (uint32_t)half != rank;
+    const uint32_t g_line0 = remote ? map_to_cta(g_line_local, (uint32_t)half) : g_line_local;   // + buf * 32 KB
+    float mu0 = 0.f, x_min = 0.f, x_max = 0.f;
+    if (has_col) {
+      mu0 = p.mu0[0];
+      const float2 xm = __ldg(reinterpret_cast<const float2*>(p.xmm) + (blockIdx.x >> 1));
+      x_min = xm.x; x_max = xm.y;
+    }
+    const bool x_ok = has_col && fabsf(x_min - mu0) <= 120.f && fabsf(x_max - mu0) <= 120.f;
+    for (int st = 0; st < nsteps; ++st) {
+      const int buf = st & 1;
+      const uint32_t bph = (st >> 1) & 1;
+      const int64_t n0 = (int64_t)(s0 + st) * 256 + 128 * rank;      // first y of this CTA in this step
+      const int64_t yg = n0 + yl;
+      const bool y_ok = yg < p.N;
+      float ly = INFINITY, a_y = 0.f;
+      bool fast = false;
+      if (has_col) {
+        ly = __ldg(p.ly2 + yg);                                        // +inf in the padding -> P^col = 0
+        const float2 ym = __ldg(reinterpret_cast<const float2*>(p.ymm) + ((s0 + st) * 2 + (int)rank));
+        fast = x_ok && !(p.dbg & 8) && (ym.y - x_min <= 100.f) && (x_max - ym.x <= 100.f) &&
+               (!(ym.x <= ym.y) || (fabsf(ym.x - mu0) <= 120.f && fabsf(ym.y - mu0) <= 120.f));
+        if (fast) a_y = y_ok ? ex2_approx(ly - mu0) : 0.f;
+      }
+      mbar_wait(sfull_bar(buf), bph);
+      tc_fence_after();
+      // diagonal of this pair's rows: x_global + diag_off == y_global
+      const int64_t xdg = yg - p.diag_off - xg0;     // column (within this thread's 64) holding this row's positive
+      const bool special = (n0 + 128 > p.N) || (n0 + 128 > pair_row0 + p.diag_off && n0 < pair_row0 + p.diag_off + 128);
+      uint32_t g[2][16];
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t v[32];
+        tmem_ld32(lane_addr + buf * 128 + half * 64 + cc * 32, v);
+        tmem_ld_wait();
+        const int xd = (xdg >= cc * 32 && xdg < cc * 32 + 32) ? (int)(xdg - cc * 32) : -1;
+        const float* xarr = (fast ? p.bx : p.lx2) + xg0 + cc * 32;
+        if (!has_col) {
+          if (special) bwd3_chunk<2, true>(v, g[cc], k2, ly, a_y, xarr, w_diag_s, xd, y_ok);
+          else bwd3_chunk<2, false>(v, g[cc], k2, ly, a_y, xarr, w_diag_s, xd, y_ok);
+        } else if (fast) {
+          if (special) bwd3_chunk<0, true>(v, g[cc], k2, ly, a_y, xarr, w_diag_s, xd, y_ok);
+          else bwd3_chunk<0, false>(v, g[cc], k2, ly, a_y, xarr, w_diag_s, xd, y_ok);
+        } else {
+          if (special) bwd3_chunk<1, true>(v, g[cc], k2, ly, a_y, xarr, w_diag_s, xd, y_ok);
+          else bwd3_chunk<1, false>(v, g[cc], k2, ly, a_y, xarr, w_diag_s, xd, y_ok);
+        }
+      }
+      tc_fence_before();          // TMEM reads of S^T are complete
+      // G tile `buf` was last read by dX of step st-2 (in both CTAs): long done in steady state
+      mbar_wait(gempty_bar(buf), bph ^ 1);
+      const uint32_t g_line = g_line0 + buf * (4 * kTile8K);
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+#pragma unroll
+        for (int pc = 0; pc < 4; ++pc) {
+          const uint32_t piece = (uint32_t)((cc * 4 + pc) ^ (grow & 7));
+          if (remote) st_cluster_v4(g_line + piece * 16, g[cc][4 * pc], g[cc][4 * pc + 1], g[cc][4 * pc + 2], g[cc][4 * pc + 3]);
+          else st_shared_v4(g_line + piece * 16, g[cc][4 * pc], g[cc][4 * pc + 1], g[cc][4 * pc + 2], g[cc][4 * pc + 3]);
+        }
+      }
+      // generic-proxy stores (local or peer shared memory) -> tensor-core (async) proxy
+      if (p.dbg & 32) fence_proxy_async_all();
+      else if (remote) fence_proxy_async_smem_cluster();
+      else fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_release_cluster(gfull_bar(buf), 0, !leader);
+    }
+    // ---- dX^T accumulator -> global: lane = d, columns = x ----
+    mbar_wait(dxfull_bar, 0);
+    tc_fence_after();
+    const float alpha = (p.go ? p.go[0] : 1.f) * ls * p.inv_2n * (1.f / kGScale);
+    for (int h = 0; h < p.ndh; ++h) {
+      const int64_t d = (int64_t)h * 256 + 128 * rank + yl;
+#pragma unroll 1
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t v[32];
+        tmem_ld32(lane_addr + kDxCol + h * 128 + half * 64 + cc * 32, v);
+        tmem_ld_wait();
+        if (d < p.D && nsteps > 0) {
+          const int64_t x0 = xg0 + cc * 32;
+          if (p.nsplit > 1) {
+            float* dst = p.acc_ws + ((int64_t)blockIdx.y * p.M + x0) * p.D + d;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (x0 + j < p.M) dst[(int64_t)j * p.D] = __uint_as_float(v[j]);
+          } else {
+            uint16_t* dst = reinterpret_cast<uint16_t*>(p.dX) + x0 * p.lddx + d;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (x0 + j < p.M) {
+                const uint32_t pk = kBF16 ? pack_bf16x2(__uint_as_float(v[j]) * alpha, 0.f)
+                                          : pack_f16x2(__uint_as_float(v[j]) * alpha, 0.f);
+                dst[(int64_t)j * p.lddx] = (uint16_t)(pk & 0xFFFFu);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_cg2(tmem_base, kTmemCols);
+  }
+}
+
+// Row / column statistics for the transposed backward kernel (one block of 1024 threads), log2 units:
+//   lx2[x] = lse_x[x] * log2e - lw_row (+inf padded to m_pad), bx[x] = 2^(mu0 - lx2[x]) (0 padded), xmm per 128 rows
+//   ly2[y] = lse_y[y] * log2e - lw_col (+inf padded to n_pad), ymm per 128 rows;  mu0 = midpoint of the lx2 range
+__global__ void __launch_bounds__(1024)
+prep_bwd3_kernel(const float* __restrict__ lse_x, int64_t M, int64_t m_pad, float lw_row, const float* __restrict__ lse_y,
+                 int64_t N, int64_t n_pad, float lw_col, float* __restrict__ lx2, float* __restrict__ bx,
+                 float* __restrict__ xmm, float* __restrict__ ly2, float* __restrict__ ymm, float* __restrict__ mu0_out) {
+  __shared__ float red_min[32], red_max[32];
+  __shared__ float mu_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float mn = INFINITY, mx = -INFINITY;
+  for (int64_t j = tid; j < M; j += 1024) {
+    const float v = lse_x[j] * kLog2e - lw_row;
+    mn = fminf(mn, v); mx = fmaxf(mx, v);
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if (lane == 0) { red_min[warp] = mn; red_max[warp] = mx; }
+  __syncthreads();
+  if (warp == 0) {
+    mn = red_min[lane]; mx = red_max[lane];
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (lane == 0) { mu_s = 0.5f * mn + 0.5f * mx; mu0_out[0] = mu_s; }
+  }
+  __syncthreads();
+  const float mu = mu_s;
+  // 128-row blocks of x and of y, one warp per block (4 elements per lane)
+  const int64_t xb = m_pad / 128, yb = lse_y ? n_pad / 128 : 0;
+  for (int64_t b = warp; b < xb + yb; b += 32) {
+    const bool is_x = b < xb;
+    const int64_t base = (is_x ? b : b - xb) * 128;
+    const float* src = is_x ? lse_x : lse_y;
+    const int64_t lim = is_x ? M : N;
+    const float lw = is_x ? lw_row : lw_col;
+    float smn = INFINITY, smx = -INFINITY;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int64_t j = base + e * 32 + lane;
+      const bool ok = j < lim;
+      const float v = ok ? src[j] * kLog2e - lw : INFINITY;
+      if (is_x) { lx2[j] = v; bx[j] = ok ? exp2f(mu - v) : 0.f; }
+      else ly2[j] = v;
+      if (ok) { smn = fminf(smn, v); smx = fmaxf(smx, v); }
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      smn = fminf(smn, __shfl_xor_sync(0xffffffffu, smn, o));
+      smx = fmaxf(smx, __shfl_xor_sync(0xffffffffu, smx, o));
+    }
+    if (lane == 0) {
+      float* dst = is_x ? xmm + 2 * b : ymm + 2 * (b - xb);
+      dst[0] = smn; dst[1] = smx;
+    }
   }
 }
 
@@ -1494,6 +2047,17 @@ BwdPlan plan_bwd(int64_t M, int64_t N, int64_t D) {
 
 struct Bwd2Plan { int kch; int kpairs; int ndh; int steps_total; int nsplit; int steps_per_split; uint32_t smem; int cpairs; };
 
+// MCLIP_BWD_GTMEM=1 hands G to the dX MMA through TMEM (TS form, duplicated layout) instead of shared memory.
+// Numerically identical; measured slower (1.61 vs 1.53 ms at 32768^2 x 512) because of the extra exchange + barriers.
+bool g_in_tmem() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("MCLIP_BWD_GTMEM");
+    cached = (e && e[0] == '1') ? 1 : 0;
+  }
+  return cached == 1;
+}
+
 // Pairs per cluster.  Default 1: the pair kernel is limited by the ~64 B/clk each SM can ingest from L2, which
 // multicast does not reduce (measured: 1.95 ms with 2 pairs + multicast vs 1.85 ms with 1 pair at 32768^2 x 512,
 // and 4-CTA clusters strand 16 of the 148 SMs).  MCLIP_BWD_PAIRS=2 selects the multicast variant.
@@ -1563,14 +2127,19 @@ bool tc_supported(int64_t M, int64_t N, int64_t D, int64_t ldx, int64_t ldy, int
 
 size_t tc_row_lse_ws(int64_t M, int64_t N, int64_t D) {
   const FwdPlan f = fwd_uses_pair(D) ? plan_fwd2(M, N, D) : plan_fwd(M, N, D);
-  return align_up((size_t)f.nsplit * M * 2 * sizeof(float), 256);
+  return align_up((size_t)f.nsplit * M * 3 * sizeof(float), 256);
 }
 
 size_t tc_block_grad_ws(int64_t M, int64_t N, int64_t D) {
   if (D <= 512) {
     const Bwd2Plan b = plan_bwd2(M, N, D);
-    // dtype is not known here: always reserve room for the f16 copy of Y
-    return bwd_ws_layout(b.nsplit, M, N, D, (int64_t)b.steps_total * 256, true).total;
+    // dtype is not known here: always reserve room for the f16 copy of Y; cover both pair kernels
+    const size_t v2 = bwd_ws_layout(b.nsplit, M, N, D, (int64_t)b.steps_total * 256, true).total;
+    const int64_t n_pad = (int64_t)b.steps_total * 256, m_pad = ceil_div(M, 128) * 128;
+    const size_t v3 = (b.nsplit > 1 ? align_up((size_t)b.nsplit * M * D * sizeof(float), 256) : 0) +
+                      align_up(((size_t)2 * m_pad + 2 * (m_pad / 128) + n_pad + 2 * (n_pad / 128) + 64) * sizeof(float), 256) +
+                      align_up((size_t)N * D * 2, 256);
+    return v2 > v3 ? v2 : v3;
   }
   const BwdPlan b = plan_bwd(M, N, D);
   return (b.nsplit > 1 ? align_up((size_t)b.nsplit * M * (D + 1) * sizeof(float), 256) : 0) + align_up((size_t)N * D * 2, 256);
@@ -1591,6 +2160,7 @@ int tc_row_lse(const RowLseArgs& a) {
   p.tiles_per_split = f.tiles_per_split; p.diag_off = a.diag_off; p.ls = a.logit_scale;
   p.part_m2 = reinterpret_cast<float*>(a.ws);
   p.part_s = p.part_m2 + (size_t)f.nsplit * a.M;
+  p.part_c = a.rowdot ? p.part_s + (size_t)f.nsplit * a.M : nullptr;
   p.diag = a.diag; p.bf16 = a.dtype == MCLIP_DTYPE_BF16;
   {
     const char* e = getenv("MCLIP_DBG");
@@ -1625,7 +2195,98 @@ int tc_row_lse(const RowLseArgs& a) {
   }
   count_launch();
   MCLIP_CUDA_OK(cudaGetLastError());
-  return launch_lse_merge(p.part_m2, p.part_s, f.nsplit, a.M, a.lse, a.stream);
+  return launch_lse_merge(p.part_m2, p.part_s, p.part_c, f.nsplit, a.M, a.lse, a.rowdot, a.stream);
+}
+
+// transposed CTA-pair backward (D <= 512, no rowdot output)
+int tc_block_grad3(const BlockGradArgs& a) {
+  const Bwd2Plan b = plan_bwd2(a.M, a.N, a.D);
+  const bool bf = a.dtype == MCLIP_DTYPE_BF16;
+  const int64_t n_pad = (int64_t)b.steps_total * 256;
+  const int64_t m_pad = ceil_div(a.M, 128) * 128;
+  // workspace: [acc partials][stats: lx2, bx, xmm, ly2, ymm, mu0][Y16]
+  const size_t acc_bytes = b.nsplit > 1 ? align_up((size_t)b.nsplit * a.M * a.D * sizeof(float), 256) : 0;
+  const size_t stat_floats = (size_t)2 * m_pad + 2 * (m_pad / 128) + n_pad + 2 * (n_pad / 128) + 64;
+  const size_t stat_bytes = align_up(stat_floats * sizeof(float), 256);
+  const size_t y16_bytes = bf ? align_up((size_t)a.N * a.D * 2, 256) : 0;
+  if (acc_bytes + stat_bytes + y16_bytes > a.ws_bytes) { set_error("block_grad(tcgen05): workspace %zu < %zu", a.ws_bytes, acc_bytes + stat_bytes + y16_bytes); return MCLIP_ERR_WORKSPACE; }
+  uint8_t* ws = reinterpret_cast<uint8_t*>(a.ws);
+  float* lx2 = reinterpret_cast<float*>(ws + acc_bytes);
+  float* bx = lx2 + m_pad;
+  float* xmm = bx + m_pad;
+  float* ly2 = xmm + 2 * (m_pad / 128);
+  float* ymm = ly2 + n_pad;
+  float* mu0 = ymm + 2 * (n_pad / 128);
+  const bool has_col = a.w_col != 0.f;
+  prep_bwd3_kernel<<<1, 1024, 0, a.stream>>>(a.lse_x, a.M, m_pad, log2f(a.w_row) + 12.f, has_col ? a.lse_y : nullptr, a.N, n_pad,
+                                             has_col ? log2f(a.w_col) + 12.f : 0.f, lx2, bx, xmm, ly2, ymm, mu0);
+  count_launch();
+  MCLIP_CUDA_OK(cudaGetLastError());
+  const void* y16 = a.Y;
+  int64_t ld16 = a.ldy;
+  if (bf) {
+    __half* dst = reinterpret_cast<__half*>(ws + acc_bytes + stat_bytes);
+    const int64_t n8 = a.N * (a.D / 8);
+    const unsigned blocks = (unsigned)(ceil_div(n8, 256) < 148 * 8 ? ceil_div(n8, 256) : 148 * 8);
+    bf16_to_f16_kernel<<<blocks, 256, 0, a.stream>>>(reinterpret_cast<const __nv_bfloat16*>(a.Y), a.N, a.D, a.ldy, dst);
+    count_launch();
+    MCLIP_CUDA_OK(cudaGetLastError());
+    y16 = dst;
+    ld16 = a.D;
+  }
+  CUtensorMap tmX, tmY, tmY16;
+  int rc = make_tmap(&tmX, a.X, a.M, a.D, a.ldx, a.dtype, 64);
+  if (rc) return rc;
+  rc = make_tmap(&tmY, a.Y, a.N, a.D, a.ldy, a.dtype, 128);
+  if (rc) return rc;
+  rc = make_tmap(&tmY16, y16, a.N, a.D, ld16, MCLIP_DTYPE_F16, 128);
+  if (rc) return rc;
+  Bwd3Params p;
+  p.M = a.M; p.N = a.N; p.D = a.D; p.kpairs = b.kpairs; p.ndh = b.ndh; p.steps_total = b.steps_total;
+  p.steps_per_split = b.steps_per_split; p.nsplit = b.nsplit; p.diag_off = a.diag_off; p.ls = a.logit_scale; p.go = a.grad_out;
+  p.lx2 = lx2; p.bx = bx; p.xmm = xmm; p.ly2 = ly2; p.ymm = ymm; p.mu0 = mu0; p.w_diag = a.w_diag; p.inv_2n = a.inv_2n;
+  p.has_col = has_col ? 1 : 0; p.dX = a.dX; p.lddx = a.lddx; p.acc_ws = reinterpret_cast<float*>(ws);
+  {
+    const char* e = getenv("MCLIP_DBG");
+    p.dbg = e ? atoi(e) : 0;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * ceil_div(a.M, 128)), (unsigned)b.nsplit);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = b.smem;
+  cfg.stream = a.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (bf) {
+    rc = set_smem(tc_block_grad3_kernel<true>, b.smem);
+    if (rc) return rc;
+    MCLIP_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_block_grad3_kernel<true>, tmX, tmY, tmY16, p));
+  } else {
+    rc = set_smem(tc_block_grad3_kernel<false>, b.smem);
+    if (rc) return rc;
+    MCLIP_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_block_grad3_kernel<false>, tmX, tmY, tmY16, p));
+  }
+  count_launch();
+  MCLIP_CUDA_OK(cudaGetLastError());
+  if (b.nsplit > 1) {
+    const int64_t n = a.M * a.D;
+    const unsigned blocks = (unsigned)(ceil_div(n, 1024) < 148 * 8 ? ceil_div(n, 1024) : 148 * 8);
+    const float scale = a.inv_2n * (1.f / kGScale);
+    if (bf)
+      acc_to_dx_kernel<__nv_bfloat16><<<blocks, 256, 0, a.stream>>>(p.acc_ws, nullptr, b.nsplit, a.M, a.D, a.logit_scale, a.grad_out,
+                                                                   scale, reinterpret_cast<__nv_bfloat16*>(a.dX), a.lddx, nullptr);
+    else
+      acc_to_dx_kernel<__half><<<blocks, 256, 0, a.stream>>>(p.acc_ws, nullptr, b.nsplit, a.M, a.D, a.logit_scale, a.grad_out, scale,
+                                                            reinterpret_cast<__half*>(a.dX), a.lddx, nullptr);
+    count_launch();
+    MCLIP_CUDA_OK(cudaGetLastError());
+  }
+  return MCLIP_OK;
 }
 
 // CTA-pair backward (D <= 512)
@@ -1687,16 +2348,20 @@ int tc_block_grad2(const BlockGradArgs& a) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-#define MCLIP_LAUNCH_BWD2(BF, PAIRS)                                                        \
+#define MCLIP_LAUNCH_BWD2(BF, PAIRS, GT)                                                    \
   do {                                                                                      \
-    rc = set_smem(tc_block_grad2_kernel<BF, PAIRS>, b.smem);                                \
+    rc = set_smem(tc_block_grad2_kernel<BF, PAIRS, GT>, b.smem);                            \
     if (rc) return rc;                                                                      \
-    MCLIP_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_block_grad2_kernel<BF, PAIRS>, tmX, tmY, tmY16, p)); \
+    MCLIP_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_block_grad2_kernel<BF, PAIRS, GT>, tmX, tmY, tmY16, p)); \
   } while (0)
-  if (bf && b.cpairs == 2) MCLIP_LAUNCH_BWD2(true, 2);
-  else if (bf) MCLIP_LAUNCH_BWD2(true, 1);
-  else if (b.cpairs == 2) MCLIP_LAUNCH_BWD2(false, 2);
-  else MCLIP_LAUNCH_BWD2(false, 1);
+  const bool gt = g_in_tmem();
+  if (b.cpairs == 2) {            // multicast variant: shared-memory G only
+    if (bf) MCLIP_LAUNCH_BWD2(true, 2, false); else MCLIP_LAUNCH_BWD2(false, 2, false);
+  } else if (gt) {
+    if (bf) MCLIP_LAUNCH_BWD2(true, 1, true); else MCLIP_LAUNCH_BWD2(false, 1, true);
+  } else {
+    if (bf) MCLIP_LAUNCH_BWD2(true, 1, false); else MCLIP_LAUNCH_BWD2(false, 1, false);
+  }
 #undef MCLIP_LAUNCH_BWD2
   count_launch();
   MCLIP_CUDA_OK(cudaGetLastError());
@@ -1721,7 +2386,14 @@ int tc_block_grad2(const BlockGradArgs& a) {
 int tc_block_grad(const BlockGradArgs& a) {
   if (((uintptr_t)a.X | (uintptr_t)a.Y | (uintptr_t)a.dX) & 15) { set_error("block_grad(tcgen05): X/Y/dX must be 16-byte aligned"); return MCLIP_ERR_INVALID; }
   if (!(a.w_row > 0.f) || a.w_col < 0.f) { set_error("block_grad(tcgen05): needs w_row > 0 and w_col >= 0"); return MCLIP_ERR_INVALID; }
-  if (a.D <= 512 && !use_single_cta_bwd()) return tc_block_grad2(a);
+  if (a.D <= 512 && !use_single_cta_bwd()) {
+    // MCLIP_BWD_V3=1 selects the transposed pair kernel (numerically identical, no rowdot output).  It makes both
+    // MMAs math-bound but needs half of G pushed into the peer's shared memory every step; measured 1.98 ms vs
+    // 1.65 ms for the non-transposed kernel at 32768^2 x 512, so the latter stays the default.
+    const char* e = getenv("MCLIP_BWD_V3");
+    const bool v3 = (e && e[0] == '1') && a.rowdot == nullptr;
+    return v3 ? tc_block_grad3(a) : tc_block_grad2(a);
+  }
   const BwdPlan b = plan_bwd(a.M, a.N, a.D);
   if (b.stages < 2) { set_error("block_grad(tcgen05): not enough shared memory for D=%lld", (long long)a.D); return MCLIP_ERR_UNSUPPORTED; }
   const bool bf = a.dtype == MCLIP_DTYPE_BF16;

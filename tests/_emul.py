@@ -11,10 +11,15 @@ class EmulatedBackend:
     def __init__(self):
         self.calls = []
 
-    def row_lse(self, X, Y, ls, diag_off, want_diag):
+    def row_lse(self, X, Y, ls, diag_off, want_diag, want_rowdot=False):
         self.calls.append("row_lse")
         lse, diag = O.block_row_lse(X, Y, float(ls), diag_off)
-        return lse.float(), (diag.float() if want_diag else None)
+        out = (lse.float(), (diag.float() if want_diag else None))
+        if want_rowdot:
+            C = X.double() @ Y.double().T
+            P = torch.exp(float(ls) * C - lse[:, None])
+            out = out + ((P * C).sum(dim=1).float(),)
+        return out
 
     def block_grad(self, X, Y, ls, go, lse_x, lse_y, diag_off, w_row, w_col, w_diag, inv_2n, want_rowdot=True):
         self.calls.append("block_grad")

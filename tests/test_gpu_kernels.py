@@ -74,6 +74,12 @@ def test_row_lse(path, dtype, M, N, D, ls, diag_off):
     assert float((diag.cpu().double() - ref_diag).abs().max()) <= 2e-6
     lse2, none = be.row_lse(xd, yd, lsd, diag_off, False)
     assert none is None and torch.equal(lse2, lse)       # deterministic, diag optional
+    lse3, _, rowdot = be.row_lse(xd, yd, lsd, diag_off, False, True)
+    C = x.double() @ y.double().T
+    ref_rd = (torch.exp(ls * C - ref_lse[:, None]) * C).sum(dim=1)
+    rd_tol = (4 * 1.2e-7 * max(1.0, abs(ls)) + 1e-6) if dtype == torch.float32 else 2e-3
+    assert torch.equal(lse3, lse)
+    assert float((rowdot.cpu().double() - ref_rd).abs().max()) <= rd_tol * max(1.0, float(ref_rd.abs().max()))
 
 
 def test_row_lse_strided_rows():
@@ -112,8 +118,10 @@ GRAD_CASES = [
 ]
 
 
+@pytest.mark.parametrize("want_rowdot", [True, False], ids=["rowdot", "norowdot"])
 @pytest.mark.parametrize("path,dtype,M,N,D,ls,diag_off,w", GRAD_CASES, ids=_ids(GRAD_CASES))
-def test_block_grad(path, dtype, M, N, D, ls, diag_off, w):
+def test_block_grad(path, dtype, M, N, D, ls, diag_off, w, want_rowdot):
+    """want_rowdot=False is what ClipLoss uses (rowdot comes from the forward kernel)."""
     be = backend(path)
     x, y = feats(M, N, D, dtype, seed=M * 3 + N, correlated=True)
     xf, yf = x.float(), y.float()
@@ -124,16 +132,40 @@ def test_block_grad(path, dtype, M, N, D, ls, diag_off, w):
     dev = "cuda"
     dx, rd = be.block_grad(x.to(dev), y.to(dev), torch.tensor([ls], device=dev), torch.tensor([go], device=dev),
                            lse_x.float().to(dev), lse_y.float().to(dev) if w[1] else None, diag_off,
-                           float(w[0]), float(w[1]), float(w[2]), inv_2n)
+                           float(w[0]), float(w[1]), float(w[2]), inv_2n, want_rowdot)
     torch.cuda.synchronize()
     assert dx.dtype == dtype and dx.shape == (M, D)
     tol = TOL[dtype]
     scale = go * abs(ls) * inv_2n * M ** 0.5            # natural size of dX for unit-norm rows
     err = float((dx.cpu().double() - ref_dx).norm())
     assert err <= tol * float(ref_dx.norm()) + 4 * 1.2e-7 * max(1.0, abs(ls)) * scale
+    if not want_rowdot:
+        assert rd is None
+        return
     # rowdot = sum_j P_ij c_ij: P inherits the fp32 rounding of s = ls * c (|s| up to ls), i.e. ~eps * ls relative
     rd_tol = (4 * 1.2e-7 * max(1.0, abs(ls)) + 1e-6) if dtype == torch.float32 else 2e-3
     assert float((rd.cpu().double() - ref_rd).abs().max()) <= rd_tol * max(1.0, float(ref_rd.abs().max()))
+
+
+@pytest.mark.parametrize("M,N,D,ls,diag_off,w", [(128, 256, 512, 14.2857, 0, (1, 1, 2)), (300, 1000, 384, 30.0, 17, (1, 1, 2)),
+                                                 (512, 4096, 512, 100.0, 1024, (1, 0, 1)), (2048, 2048, 512, 14.2857, 0, (1, 1, 2))])
+def test_block_grad_transposed_pair_kernel(M, N, D, ls, diag_off, w, monkeypatch):
+    """MCLIP_BWD_V3=1: the transposed CTA-pair kernel (G exchanged through the peer's shared memory) gives the
+    same dX as the oracle."""
+    monkeypatch.setenv("MCLIP_BWD_V3", "1")
+    be = backend(TC)
+    x, y = feats(M, N, D, torch.bfloat16, seed=M * 3 + N, correlated=True)
+    xf, yf = x.float(), y.float()
+    lse_x, _ = O.block_row_lse(xf, yf, ls, None)
+    lse_y, _ = O.block_row_lse(yf, xf, ls, None)
+    ref_dx, _ = O.block_grad(xf, yf, ls, lse_x, lse_y, diag_off, *w, alpha=3.0 * ls / (2 * M))
+    dx, rd = be.block_grad(x.cuda(), y.cuda(), torch.tensor([ls], device="cuda"), torch.tensor([3.0], device="cuda"),
+                           lse_x.float().cuda(), lse_y.float().cuda() if w[1] else None, diag_off,
+                           float(w[0]), float(w[1]), float(w[2]), 1.0 / (2 * M), False)
+    torch.cuda.synchronize()
+    scale = 3.0 * ls / (2 * M) * M ** 0.5
+    assert rd is None
+    assert float((dx.cpu().double() - ref_dx).norm()) <= 2e-3 * float(ref_dx.norm()) + 8 * 1.2e-7 * max(1.0, ls) * scale
 
 
 def load_single():

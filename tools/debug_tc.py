@@ -45,17 +45,19 @@ def run_case(kind, M, N, D, ls, diag_off, dtype, oracle):
         lx, _ = simt.row_lse(xd, yd, lsd, 0, False)
         ly, _ = simt.row_lse(yd, xd, lsd, 0, False)
         go = torch.tensor([2.0], device="cuda")
-        a, ra = tc.block_grad(xd, yd, lsd, go, lx, ly, diag_off, 1.0, 1.0, 2.0, 0.5 / M)
+        want_rd = os.environ.get("MCLIP_BWD_V3") != "1"
+        a, ra = tc.block_grad(xd, yd, lsd, go, lx, ly, diag_off, 1.0, 1.0, 2.0, 0.5 / M, want_rd)
         torch.cuda.synchronize()
         b, rb = simt.block_grad(xd, yd, lsd, go, lx, ly, diag_off, 1.0, 1.0, 2.0, 0.5 / M)
         torch.cuda.synchronize()
         af, bf = a.float(), b.float()
         rel = float((af - bf).norm() / bf.norm().clamp_min(1e-30))
-        print(f"bwd {M}x{N}x{D} ls={ls}: tc-vs-simt dX rel={rel:.3e} |simt|={float(bf.norm()):.3e} rowdot max|d|={float((ra - rb).abs().max()):.3e}"
+        rdd = float((ra - rb).abs().max()) if ra is not None else float("nan")
+        print(f"bwd {M}x{N}x{D} ls={ls}: tc-vs-simt dX rel={rel:.3e} |simt|={float(bf.norm()):.3e} rowdot max|d|={rdd:.3e}"
               f" nan={int(torch.isnan(af).sum())}")
         if oracle:
             ref, _ = O.block_grad(x.float(), y.float(), ls, lx.cpu(), ly.cpu(), diag_off, 1.0, 1.0, 2.0, 2.0 * ls * 0.5 / M)
-            print(f"  vs fp64 oracle: tc rel={O.rel_err(a.cpu(), ref):.3e}  simt rel={O.rel_err(b.cpu(), ref):.3e}  (kernel: {'1-CTA' if os.environ.get('MCLIP_BWD_1CTA') == '1' else 'CTA pair x' + os.environ.get('MCLIP_BWD_PAIRS', '2')})")
+            print(f"  vs fp64 oracle: tc rel={O.rel_err(a.cpu(), ref):.3e}  simt rel={O.rel_err(b.cpu(), ref):.3e}  (kernel: {'1-CTA' if os.environ.get('MCLIP_BWD_1CTA') == '1' else ('pair v2' if want_rd else 'pair v3 transposed')})")
         if rel > 5e-3 or torch.isnan(af).any():
             err = (af - bf).abs()
             rows = err.max(dim=1).values
@@ -79,7 +81,7 @@ def time_case(kind, M, N, D, dtype, iters):
     ly, _ = tc.row_lse(y, x, lsd, 0, False)
     go = torch.tensor([1.0], device="cuda")
     fn = (lambda: tc.row_lse(x, y, lsd, 0, True)) if kind == "fwd" else (
-        lambda: tc.block_grad(x, y, lsd, go, lx, ly, 0, 1.0, 1.0, 2.0, 0.5 / M))
+        lambda: tc.block_grad(x, y, lsd, go, lx, ly, 0, 1.0, 1.0, 2.0, 0.5 / M, os.environ.get("MCLIP_BWD_V3") != "1"))
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
@@ -100,7 +102,7 @@ CASES = [
     ("bwd", 128, 128, 64, 10.0, 0), ("bwd", 128, 128, 256, 10.0, 0), ("bwd", 128, 128, 512, 14.2857, 0),
     ("bwd", 128, 256, 512, 14.2857, 0), ("bwd", 129, 300, 512, 30.0, 64), ("bwd", 512, 4096, 512, 30.0, 1024),
     ("bwd", 300, 1000, 768, 30.0, 17), ("bwd", 64, 64, 64, 14.2857, 0), ("bwd", 1000, 3000, 384, 14.2857, 100), ("bwd", 2048, 2048, 512, 14.2857, 0),
-    ("bwd_p2", 512, 4096, 512, 30.0, 1024), ("bwd_2exp", 1000, 3000, 384, 14.2857, 100),
+    ("bwd_v3", 512, 4096, 512, 30.0, 1024), ("bwd_v3", 1000, 3000, 384, 14.2857, 100), ("bwd_2exp", 1000, 3000, 384, 14.2857, 100),
     ("fwd", 256, 256, 512, 14.2857, 0), ("fwd", 2048, 2048, 512, 100.0, 0), ("fwd", 1000, 3000, 384, 14.2857, 100),
     ("bwd", 4096, 4096, 512, 14.2857, 0), ("bwd", 640, 1111, 200, 14.2857, 300),
 ]
@@ -120,9 +122,7 @@ if __name__ == "__main__":
             run_case(a[0], int(a[1]), int(a[2]), int(a[3]), float(a[4]), int(a[5]), "bf16", int(a[1]) * int(a[2]) <= 1 << 22)
         sys.exit(0)
     if args.dbg_sweep:
-        for kind, extra in (("bwd", {"MCLIP_DBG": "0"}), ("bwd", {"MCLIP_DBG": "8"}), ("bwd", {"MCLIP_DBG": "1"}),
-                            ("bwd", {"MCLIP_DBG": "0", "MCLIP_BWD_PAIRS": "2"}),
-                            ("fwd", {}), ("fwd", {"MCLIP_FWD_1CTA": "1"})):
+        for kind, extra in (("bwd", {}), ("bwd", {"MCLIP_BWD_V3": "1"}), ("bwd", {"MCLIP_DBG": "8"}), ("bwd", {"MCLIP_DBG": "16"})):
             env = dict(os.environ, **extra)
             for shape in (("32768", "32768", "512"), ("4096", "32768", "512")):
                 r = subprocess.run([sys.executable, __file__, "--one", "time", kind, *shape], capture_output=True,
@@ -139,9 +139,9 @@ if __name__ == "__main__":
         if j[0].endswith("_1cta"):
             j = [j[0][:-5]] + j[1:]
             env["MCLIP_BWD_1CTA"] = "1"
-        if j[0].endswith("_p2"):
+        if j[0].endswith("_v3"):
             j = [j[0][:-3]] + j[1:]
-            env["MCLIP_BWD_PAIRS"] = "2"
+            env["MCLIP_BWD_V3"] = "1"
         if j[0].endswith("_2exp"):
             j = [j[0][:-5]] + j[1:]
             env["MCLIP_DBG"] = "8"
