@@ -238,23 +238,42 @@ def main():
     value = B / (ms_per_step * 1e-3)
 
     # ---- end-to-end through the public API with host buffers (H2D of the step's inputs + D2H of the loss) ----
-    a_e = torch.empty_like(img_d).requires_grad_(True)
-    b_e = torch.empty_like(txt_d).requires_grad_(True)
-    loss_h = torch.empty((), dtype=torch.float32).pin_memory()
+    # Every step's features start in pinned host memory and its loss ends in pinned host memory.  The copies of
+    # step k+1 are issued on a copy stream while step k computes (two device buffer sets), the way a training loop
+    # with non_blocking=True transfers behaves; all copies are inside the timed region.
+    copy_stream = torch.cuda.Stream(device=dev)
+    bufs = [(torch.empty_like(img_d).requires_grad_(True), torch.empty_like(txt_d).requires_grad_(True)) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    loss_h = torch.empty(args.steps + 3, dtype=torch.float32).pin_memory()
 
-    def e2e_step():
-        with torch.no_grad():
-            a_e.copy_(img_h, non_blocking=True)
-            b_e.copy_(txt_h, non_blocking=True)
-        loss = step(a_e, b_e)
-        loss_h.copy_(loss.detach(), non_blocking=True)
-    for _ in range(3):
-        e2e_step()
+    def stage_inputs(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])      # the step that last used this slot is done with it
+            with torch.no_grad():
+                bufs[slot][0].copy_(img_h, non_blocking=True)
+                bufs[slot][1].copy_(txt_h, non_blocking=True)
+            ready[slot].record(copy_stream)
+
+    def e2e_run(n):
+        main = torch.cuda.current_stream(dev)
+        for sl in range(2):
+            consumed[sl].record(main)
+        stage_inputs(0)
+        for k in range(n):
+            slot = k & 1
+            if k + 1 < n:
+                stage_inputs(slot ^ 1)
+            main.wait_event(ready[slot])
+            loss = step(*bufs[slot])
+            consumed[slot].record(main)
+            loss_h[k].copy_(loss.detach(), non_blocking=True)
+
+    e2e_run(3)
     barrier()
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s0.record()
-    for _ in range(args.steps):
-        e2e_step()
+    e2e_run(args.steps)
     s1.record()
     barrier()
     e2e_ms = torch.tensor([s0.elapsed_time(s1) / args.steps], dtype=torch.float64, device=dev)
@@ -315,7 +334,8 @@ def main():
                        "wall_s_timed_region": t_wall}),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * Bl * D * 2, "d2h_bytes_per_step": 4,
-                    "ms_per_step": float(e2e_ms)},
+                    "ms_per_step": float(e2e_ms), "last_loss": float(loss_h[args.steps - 1]),
+                    "note": "inputs from pinned host memory every step (H2D prefetched on a copy stream, double-buffered), loss copied back to pinned host memory every step"},
             "gpu_launches": launches,
             "roofline": roofline,
             "cpu_baseline": cpu_base,
