@@ -79,8 +79,9 @@ def _ptr(t: Optional[torch.Tensor]):
 
 
 class CudaBackend:
-    """Tensor-level wrapper: allocates outputs/workspace with torch, passes raw pointers + the current
-    CUDA stream to the C ABI.  No host synchronisation anywhere."""
+    """Tensor-level wrapper: allocates outputs with torch, passes raw pointers + the current CUDA stream to the C
+    ABI.  No host synchronisation anywhere.  Host overhead matters for the small, latency-bound configurations
+    (B_g = 512), so workspace sizes are cached and one scratch buffer per (device, stream) is reused."""
 
     name = "cuda"
 
@@ -88,6 +89,8 @@ class CudaBackend:
         self.lib = load_library()
         self.path = path
         self._checked = set()
+        self._ws_size = {}
+        self._ws_buf = {}
 
     # -- helpers ---------------------------------------------------------------------------------
     def _prep(self, *tensors):
@@ -104,19 +107,38 @@ class CudaBackend:
                 raise ValueError("all tensors must be on the same device")
         return dev
 
-    def _stream(self, dev):
-        return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-
-    def _workspace(self, M, N, D, dtype, op, dev):
-        n = ctypes.c_size_t(0)
-        _check(self.lib, self.lib.mclip_workspace_bytes(M, N, D, DTYPE_CODES[dtype], op, self.path, ctypes.byref(n)),
-               "mclip_workspace_bytes")
-        if n.value == 0:
+    def _workspace(self, M, N, D, dtype, op, dev, stream_ptr):
+        key = (M, N, D, dtype, op)
+        need = self._ws_size.get(key)
+        if need is None:
+            n = ctypes.c_size_t(0)
+            _check(self.lib, self.lib.mclip_workspace_bytes(M, N, D, DTYPE_CODES[dtype], op, self.path, ctypes.byref(n)),
+                   "mclip_workspace_bytes")
+            need = self._ws_size[key] = n.value
+        if need == 0:
             return None, 0
-        return torch.empty(n.value, dtype=torch.uint8, device=dev), n.value
+        # the library only uses the scratch inside the launches of one call, all on `stream_ptr`: reuse is stream-ordered
+        bkey = (dev.index, stream_ptr)
+        buf = self._ws_buf.get(bkey)
+        if buf is None or buf.numel() < need:
+            buf = self._ws_buf[bkey] = torch.empty(need, dtype=torch.uint8, device=dev)
+        return buf, need
 
     def launch_count(self) -> int:
         return int(self.lib.mclip_launch_count())
+
+    class _DeviceGuard:
+        """`with torch.cuda.device(dev)` only when `dev` is not already current (the context manager is slow)."""
+        def __init__(self, dev):
+            self.ctx = None if dev.index == torch.cuda.current_device() else torch.cuda.device(dev)
+
+        def __enter__(self):
+            if self.ctx is not None:
+                self.ctx.__enter__()
+
+        def __exit__(self, *a):
+            if self.ctx is not None:
+                self.ctx.__exit__(*a)
 
     # -- ops -------------------------------------------------------------------------------------
     def row_lse(self, X: torch.Tensor, Y: torch.Tensor, ls: torch.Tensor, diag_off: int, want_diag: bool,
@@ -125,14 +147,17 @@ class CudaBackend:
         dev = self._prep(X, Y, ls)
         M, D = X.shape
         N = Y.shape[0]
-        lse = torch.empty(M, dtype=torch.float32, device=dev)
-        diag = torch.empty(M, dtype=torch.float32, device=dev) if want_diag else None
-        rowdot = torch.empty(M, dtype=torch.float32, device=dev) if want_rowdot else None
-        ws, nws = self._workspace(M, N, D, X.dtype, OP_ROW_LSE, dev)
-        with torch.cuda.device(dev):
+        nout = 1 + int(want_diag) + int(want_rowdot)
+        out = torch.empty((nout, M), dtype=torch.float32, device=dev)
+        lse = out[0]
+        diag = out[1] if want_diag else None
+        rowdot = out[nout - 1] if want_rowdot else None
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        ws, nws = self._workspace(M, N, D, X.dtype, OP_ROW_LSE, dev, stream)
+        with self._DeviceGuard(dev):
             rc = self.lib.mclip_row_lse(_ptr(X), _ptr(Y), M, N, D, X.stride(0), Y.stride(0), DTYPE_CODES[X.dtype],
                                         _ptr(ls), diag_off, _ptr(lse), _ptr(diag), _ptr(rowdot), _ptr(ws), nws,
-                                        self.path, self._stream(dev))
+                                        self.path, ctypes.c_void_p(stream))
         _check(self.lib, rc, "mclip_row_lse")
         return (lse, diag, rowdot) if want_rowdot else (lse, diag)
 
@@ -142,21 +167,22 @@ class CudaBackend:
         N = Y.shape[0]
         dX = torch.empty((M, D), dtype=X.dtype, device=dev)
         rowdot = torch.empty(M, dtype=torch.float32, device=dev) if want_rowdot else None
-        ws, nws = self._workspace(M, N, D, X.dtype, OP_BLOCK_GRAD, dev)
-        with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        ws, nws = self._workspace(M, N, D, X.dtype, OP_BLOCK_GRAD, dev, stream)
+        with self._DeviceGuard(dev):
             rc = self.lib.mclip_block_grad(_ptr(X), _ptr(Y), M, N, D, X.stride(0), Y.stride(0), DTYPE_CODES[X.dtype],
                                            _ptr(ls), _ptr(go), _ptr(lse_x), _ptr(lse_y), diag_off, w_row, w_col,
                                            w_diag, inv_2n, _ptr(dX), dX.stride(0), _ptr(rowdot), _ptr(ws), nws,
-                                           self.path, self._stream(dev))
+                                           self.path, ctypes.c_void_p(stream))
         _check(self.lib, rc, "mclip_block_grad")
         return dX, rowdot
 
     def loss_finalize(self, row_lse, col_lse, diag, ls):
         dev = self._prep(row_lse, col_lse, diag, ls)
         out = torch.empty((), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with self._DeviceGuard(dev):
             rc = self.lib.mclip_loss_finalize(_ptr(row_lse), _ptr(col_lse), _ptr(diag), row_lse.numel(), _ptr(ls),
-                                              _ptr(out), self._stream(dev))
+                                              _ptr(out), ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
         _check(self.lib, rc, "mclip_loss_finalize")
         return out
 
@@ -164,9 +190,10 @@ class CudaBackend:
         dev = self._prep(u, v, diag)
         out = torch.empty(2, dtype=torch.float32, device=dev)
         t_out, dls_out = out[0:1], out[1:2]
-        with torch.cuda.device(dev):
+        with self._DeviceGuard(dev):
             rc = self.lib.mclip_dls_finalize(_ptr(u), _ptr(v), _ptr(diag), u.numel(), _ptr(go), float(scale),
-                                             _ptr(t_out), _ptr(dls_out), self._stream(dev))
+                                             _ptr(t_out), _ptr(dls_out),
+                                             ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
         _check(self.lib, rc, "mclip_dls_finalize")
         return out[0], out[1]
 

@@ -46,7 +46,7 @@ def _compute_dtype(t: torch.Tensor) -> torch.dtype:
     """dtype the kernels run in.  Inside an autocast region fp32 features are rounded to the autocast
     dtype, which is what the reference's `@` does there; otherwise the input dtype."""
     if t.dtype == torch.float32 and t.is_cuda and torch.is_autocast_enabled():
-        ac = torch.get_autocast_gpu_dtype()
+        ac = torch.get_autocast_dtype("cuda")
         if ac in (torch.bfloat16, torch.float16):
             return ac
     if t.dtype in _SUPPORTED:
@@ -99,7 +99,7 @@ class ClipLossFunction(torch.autograd.Function):
             # the LSE vectors of the other ranks are only needed by backward: start the gather now, wait there
             stats, ctx.stats_work = _gather_rows_async(torch.stack((row_lse, col_lse)).unsqueeze(0), W, group)  # [W, 2, B_l]
         else:
-            stats = torch.stack((row_lse, col_lse)).unsqueeze(0)
+            stats = None   # W == 1, or own-row terms only: the local vectors are all backward needs
 
         # `stats` is written by the in-flight collective, so it is kept off autograd's version tracking
         ctx.stats = stats
@@ -118,8 +118,11 @@ class ClipLossFunction(torch.autograd.Function):
         if ctx.stats_work is not None:
             ctx.stats_work.wait()
             ctx.stats_work = None
-        row_lse_all = stats[:, 0, :].reshape(-1)
-        col_lse_all = stats[:, 1, :].reshape(-1)
+        if stats is not None:
+            row_lse_all = stats[:, 0, :].reshape(-1)
+            col_lse_all = stats[:, 1, :].reshape(-1)
+        else:
+            row_lse_all, col_lse_all = row_lse, col_lse
         Bl = xi.shape[0]
         Bg = W * Bl
         go = grad_out.detach().to(device=xi.device, dtype=torch.float32).reshape(1).contiguous()

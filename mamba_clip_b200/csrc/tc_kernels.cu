@@ -12,6 +12,8 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
+#include <unordered_map>
 
 #include "common.cuh"
 #include "sm100_ptx.cuh"
@@ -2109,9 +2111,19 @@ BwdWs bwd_ws_layout(int nsplit, int64_t M, int64_t N, int64_t D, int64_t n_pad, 
   return w;
 }
 
+// cudaFuncSetAttribute once per (kernel, device) and size high-water mark instead of on every launch
 template <typename K>
 int set_smem(K kernel, uint32_t bytes) {
+  static std::mutex mu;
+  static std::unordered_map<uint64_t, uint32_t> done;
+  int dev = 0;
+  MCLIP_CUDA_OK(cudaGetDevice(&dev));
+  const uint64_t key = (uint64_t)reinterpret_cast<uintptr_t>(reinterpret_cast<const void*>(kernel)) ^ ((uint64_t)dev << 56);
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = done.find(key);
+  if (it != done.end() && it->second >= bytes) return MCLIP_OK;
   MCLIP_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  done[key] = bytes;
   return MCLIP_OK;
 }
 
