@@ -99,6 +99,18 @@ int mclip_loss_finalize(const float* row_lse, const float* col_lse, const float*
 int mclip_dls_finalize(const float* u, const float* v, const float* diag, int64_t n, const float* grad_out,
                        float scale, float* t_out, float* dls_out, void* cuda_stream);
 
+/*
+ * Producer epilogue (next row of the scope table): y = cast(x / max(||x||_2, eps)) per row, f32 in, `out_dtype` out.
+ * Replaces F.normalize(features, dim=-1) of reference model.py:1011-1017 plus the rounding autocast applies in front
+ * of the logits matmul.  `inv_norm` ([M] f32, may be NULL) receives 1 / max(||x||, eps).
+ */
+int mclip_normalize_rows(const float* x, int64_t M, int64_t D, int64_t ldx, float eps, int out_dtype, void* y, int64_t ldy,
+                         float* inv_norm, void* cuda_stream);
+
+/* Backward of mclip_normalize_rows: dx = (g - n <n, g>) / ||x|| with n = x / ||x|| (g / eps where the norm was clamped). */
+int mclip_normalize_rows_bwd(const float* x, const void* g, int64_t M, int64_t D, int64_t ldx, int64_t ldg, int g_dtype,
+                             float eps, float* dx, int64_t lddx, void* cuda_stream);
+
 /* Number of kernel launches issued by this library on the calling thread since load (bench.py's
  * "gpu_launches" counter). */
 int64_t mclip_launch_count(void);

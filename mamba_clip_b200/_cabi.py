@@ -38,6 +38,11 @@ _SIGNATURES = {
     "mclip_loss_finalize": (ctypes.c_int, [_c_f32p, _c_f32p, _c_f32p, ctypes.c_int64, _c_f32p, _c_f32p, ctypes.c_void_p]),
     "mclip_dls_finalize": (ctypes.c_int, [_c_f32p, _c_f32p, _c_f32p, ctypes.c_int64, _c_f32p, ctypes.c_float, _c_f32p,
                                           _c_f32p, ctypes.c_void_p]),
+    "mclip_normalize_rows": (ctypes.c_int, [_c_f32p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_float, ctypes.c_int,
+                                            ctypes.c_void_p, ctypes.c_int64, _c_f32p, ctypes.c_void_p]),
+    "mclip_normalize_rows_bwd": (ctypes.c_int, [_c_f32p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                                ctypes.c_int64, ctypes.c_int, ctypes.c_float, _c_f32p, ctypes.c_int64,
+                                                ctypes.c_void_p]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
@@ -185,6 +190,27 @@ class CudaBackend:
                                               _ptr(out), ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
         _check(self.lib, rc, "mclip_loss_finalize")
         return out
+
+    def normalize_rows(self, x, out_dtype, eps):
+        dev = self._prep(x)
+        M, D = x.shape
+        y = torch.empty((M, D), dtype=out_dtype, device=dev)
+        with self._DeviceGuard(dev):
+            rc = self.lib.mclip_normalize_rows(_ptr(x), M, D, x.stride(0), float(eps), DTYPE_CODES[out_dtype], _ptr(y),
+                                               y.stride(0), None, ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        _check(self.lib, rc, "mclip_normalize_rows")
+        return y
+
+    def normalize_rows_bwd(self, x, g, eps):
+        dev = self._prep(x, g)
+        M, D = x.shape
+        dx = torch.empty((M, D), dtype=torch.float32, device=dev)
+        with self._DeviceGuard(dev):
+            rc = self.lib.mclip_normalize_rows_bwd(_ptr(x), _ptr(g), M, D, x.stride(0), g.stride(0), DTYPE_CODES[g.dtype],
+                                                   float(eps), _ptr(dx), dx.stride(0),
+                                                   ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        _check(self.lib, rc, "mclip_normalize_rows_bwd")
+        return dx
 
     def dls_finalize(self, u, v, diag, go, scale):
         dev = self._prep(u, v, diag)

@@ -136,4 +136,16 @@ int mclip_dls_finalize(const float* u, const float* v, const float* diag, int64_
   return launch_dls_finalize(u, v, diag, n, grad_out, scale, t_out, dls_out, (cudaStream_t)cuda_stream);
 }
 
+int mclip_normalize_rows(const float* x, int64_t M, int64_t D, int64_t ldx, float eps, int out_dtype, void* y, int64_t ldy,
+                         float* inv_norm, void* cuda_stream) {
+  if (!x || !y || M <= 0 || D <= 0 || ldx < D || ldy < D || !valid_dtype(out_dtype) || !(eps > 0.f)) { set_error("normalize_rows: invalid argument"); return MCLIP_ERR_INVALID; }
+  return launch_normalize_rows(x, M, D, ldx, eps, out_dtype, y, ldy, inv_norm, (cudaStream_t)cuda_stream);
+}
+
+int mclip_normalize_rows_bwd(const float* x, const void* g, int64_t M, int64_t D, int64_t ldx, int64_t ldg, int g_dtype,
+                             float eps, float* dx, int64_t lddx, void* cuda_stream) {
+  if (!x || !g || !dx || M <= 0 || D <= 0 || ldx < D || ldg < D || lddx < D || !valid_dtype(g_dtype) || !(eps > 0.f)) { set_error("normalize_rows_bwd: invalid argument"); return MCLIP_ERR_INVALID; }
+  return launch_normalize_rows_bwd(x, g, M, D, ldx, ldg, g_dtype, eps, dx, lddx, (cudaStream_t)cuda_stream);
+}
+
 }  // extern "C"

@@ -80,6 +80,12 @@ int launch_loss_finalize(const float* row_lse, const float* col_lse, const float
 int launch_dls_finalize(const float* u, const float* v, const float* diag, int64_t n, const float* grad_out,
                         float scale, float* t_out, float* dls_out, cudaStream_t stream);
 
+// producer epilogue (normalise + cast) -- producer_kernels.cu
+int launch_normalize_rows(const float* x, int64_t M, int64_t D, int64_t ldx, float eps, int out_dtype, void* y, int64_t ldy,
+                          float* inv_norm, cudaStream_t stream);
+int launch_normalize_rows_bwd(const float* x, const void* g, int64_t M, int64_t D, int64_t ldx, int64_t ldg, int g_dtype,
+                              float eps, float* dx, int64_t lddx, cudaStream_t stream);
+
 // ---- dtype helpers -------------------------------------------------------------------------
 template <typename T> __device__ __forceinline__ float to_f32(T v);
 template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }

@@ -1,0 +1,80 @@
+"""The "next" rows of the scope table at the same parity bar: the producer epilogue
+(F.normalize + cast, reference model.py:1011-1017) and the eval-time contrastive loss (eval.py:107-116)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import clip_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("B,D,dtype", [(64, 512, torch.bfloat16), (129, 768, torch.float16), (7, 33, torch.float32),
+                                       (4096, 512, torch.bfloat16)])
+def test_normalize_features_forward_backward(B, D, dtype):
+    from mamba_clip_b200.producer import normalize_features
+    g = torch.Generator().manual_seed(B + D)
+    x = (torch.randn(B, D, generator=g) * 3.0).cuda().requires_grad_(True)
+    y = normalize_features(x, dtype)
+    ref = F.normalize(x.detach().double(), dim=-1)
+    assert y.dtype == dtype and y.shape == (B, D)
+    tol = 1e-6 if dtype == torch.float32 else 2e-3
+    assert O.rel_err(y.cpu(), ref.cpu()) <= tol
+    go = torch.randn(B, D, generator=g).to(dtype).cuda()
+    y.backward(go)
+    xr = x.detach().double().requires_grad_(True)
+    F.normalize(xr, dim=-1).backward(go.double())
+    assert x.grad.dtype == torch.float32
+    assert O.rel_err(x.grad.cpu(), xr.grad.cpu()) <= 1e-5
+
+
+def test_zero_rows_follow_torch_eps_semantics():
+    from mamba_clip_b200.producer import normalize_features
+    x = torch.zeros(4, 64, device="cuda")
+    x[1] = 1.0
+    x.requires_grad_(True)
+    y = normalize_features(x, torch.float32)
+    assert torch.equal(y[0], torch.zeros(64, device="cuda"))           # 0 / max(0, eps) = 0, as F.normalize
+    assert abs(float(y[1].norm()) - 1.0) < 1e-6
+    y.sum().backward()
+    assert torch.isfinite(x.grad).all()
+
+
+def test_producer_into_loss_chain_matches_fp64_chain():
+    """raw fp32 projections -> normalize_features(bf16) -> ClipLoss: gradient w.r.t. the raw projections."""
+    from mamba_clip_b200 import ClipLoss
+    from mamba_clip_b200.producer import normalize_features
+    B, D, ls = 512, 512, 20.0
+    g = torch.Generator().manual_seed(3)
+    raw_i = torch.randn(B, D, generator=g)
+    raw_t = raw_i + 0.3 * torch.randn(B, D, generator=g)
+    a = raw_i.cuda().requires_grad_(True)
+    b = raw_t.cuda().requires_grad_(True)
+    loss = ClipLoss()(normalize_features(a), normalize_features(b), torch.tensor(ls, device="cuda"), output_dict=False)
+    loss.backward()
+    ad = raw_i.double().requires_grad_(True)
+    bd = raw_t.double().requires_grad_(True)
+    ni, nt = F.normalize(ad, dim=-1), F.normalize(bd, dim=-1)
+    # same bf16 rounding of the normalised features as the fused path (straight-through for the gradient)
+    ni = ni + (ni.detach().float().bfloat16().double() - ni.detach())
+    nt = nt + (nt.detach().float().bfloat16().double() - nt.detach())
+    logits = ls * ni @ nt.T
+    lab = torch.arange(B)
+    ref = (F.cross_entropy(logits, lab) + F.cross_entropy(logits.T, lab)) / 2
+    ref.backward()
+    assert abs(float(loss.detach()) - float(ref)) <= 2e-3 * abs(float(ref))
+    # two 16-bit roundings on the way back (dLoss/dfeature in bf16, then through the normalisation backward)
+    assert O.rel_err(a.grad.cpu(), ad.grad) <= 3e-3
+    assert O.rel_err(b.grad.cpu(), bd.grad) <= 3e-3
+
+
+@pytest.mark.parametrize("B,D,dtype,tol", [(64, 512, torch.float32, 1e-5), (256, 512, torch.bfloat16, 2e-3),
+                                           (2000, 768, torch.bfloat16, 2e-3)])
+def test_eval_contrastive_loss(B, D, dtype, tol):
+    from mamba_clip_b200.eval import contrastive_eval_loss
+    img, txt = O.make_features(B, D, seed=B, correlated=True, dtype=dtype)
+    ls = torch.tensor([14.2857, 14.2857], device="cuda")          # eval.py:106 takes logit_scale.mean()
+    out = contrastive_eval_loss(img.cuda(), txt.cuda(), ls)
+    ref = O.ref_port_single(img.float(), txt.float(), 14.2857, need_grad=False).loss
+    assert out.dim() == 0 and not out.requires_grad
+    assert abs(float(out) - float(ref)) <= tol * abs(float(ref)) + 1e-6
