@@ -24,6 +24,15 @@ namespace {
 
 using namespace ptx;
 
+// In-kernel cycle accounting (clock64 around the mbarrier waits + printf from a few CTAs) is compiled in only with
+// -DMCLIP_PROFILE (python -m mamba_clip_b200.build --profile) and enabled at run time with MCLIP_DBG=16; release
+// builds carry no printf and no extra registers.
+#ifdef MCLIP_PROFILE
+constexpr bool kProfile = true;
+#else
+constexpr bool kProfile = false;
+#endif
+
 constexpr int kThreads = 384;
 constexpr int kEpiWarp0 = 4;
 constexpr int kEpiThreads = 256;
@@ -356,7 +365,7 @@ tc_row_lse2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       const uint32_t idesc = make_idesc_f16(p.bf16 != 0, p.bf16 != 0, 256, BN, false, false);
       mbar_wait(xfull_bar, 0);
       uint32_t it = 0;
-      const bool prof = (p.dbg & 16) != 0 && elected;
+      const bool prof = kProfile && (p.dbg & 16) != 0 && elected;
       long long t_full = 0, t_tempty = 0, t_begin = clock64();
       for (int lt = 0; lt < ntiles; ++lt) {
         const int buf = lt & 1;
@@ -408,7 +417,7 @@ tc_row_lse2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     float m2 = -INFINITY, sum = 0.f, sc = 0.f, diag_val = 0.f;
     const bool want_dot = p.part_c != nullptr;
     constexpr int kHalfCols = BN / 2;
-    const bool eprof = (p.dbg & 16) != 0 && warp == kEpiWarp0 && lane == 0;
+    const bool eprof = kProfile && (p.dbg & 16) != 0 && warp == kEpiWarp0 && lane == 0;
     long long e_wait = 0, e_begin = clock64();
     for (int lt = 0; lt < ntiles; ++lt) {
       const int buf = lt & 1;
@@ -999,7 +1008,7 @@ tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       if (leader) mbar_expect_tx(xfull_bar, 2 * 8 * kTile8K); else mbar_arrive_cluster(xfull_bar, leader_rank);
       for (int c = 0; c < 8; ++c) tma_load_2d_cg2(x_base + c * kTile8K, &tmX, c * 64, (int32_t)m0, xfull_bar);
       uint32_t it = 0;
-      const bool pprof = (p.dbg & 16) != 0;
+      const bool pprof = kProfile && (p.dbg & 16) != 0;
       long long p_empty = 0, p_begin = clock64();
       auto stage_begin = [&]() -> uint32_t {
         const int s = it % kRing2;
@@ -1065,7 +1074,7 @@ tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       const uint32_t idesc_dx = make_idesc_f16(false, false, 128, 256, false, true);
       mbar_wait(xfull_bar, 0);
       uint32_t it = 0;
-      const bool prof = (p.dbg & 16) != 0 && elected;
+      const bool prof = kProfile && (p.dbg & 16) != 0 && elected;
       long long t_full = 0, t_gfull = 0, t_begin = clock64();
       auto stage_wait = [&]() -> uint32_t {
         const int s = it % kRing2;
@@ -1200,7 +1209,7 @@ tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       }
       a_ok = fabsf(lx_max - mu0) <= 120.f && fabsf(lx_min - mu0) <= 120.f;
     }
-    const bool eprof = (p.dbg & 16) != 0 && warp == kEpiWarp0 && lane == 0;
+    const bool eprof = kProfile && (p.dbg & 16) != 0 && warp == kEpiWarp0 && lane == 0;
     long long e_sfull = 0, e_gempty = 0, e_begin = clock64();
     for (int st = 0; st < nsteps; ++st) {
       const int buf = st & 1;
@@ -1622,7 +1631,7 @@ tc_block_grad3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       const uint32_t idesc_dx = make_idesc_f16(false, false, 256, 128, true, true);
       mbar_wait(xfull_bar, 0);
       uint32_t it = 0;
-      const bool prof = (p.dbg & 16) != 0 && elected;
+      const bool prof = kProfile && (p.dbg & 16) != 0 && elected;
       long long t_full = 0, t_gfull = 0, t_begin = clock64();
       auto stage_wait = [&]() -> uint32_t {
         const int s = it % kRing3;

