@@ -23,11 +23,11 @@
 extern "C" {
 #endif
 
-#define MCLIP_ABI_VERSION 2
+#define MCLIP_ABI_VERSION 3
 
 enum { MCLIP_DTYPE_F32 = 0, MCLIP_DTYPE_BF16 = 1, MCLIP_DTYPE_F16 = 2 };
 enum { MCLIP_PATH_AUTO = 0, MCLIP_PATH_SIMT = 1, MCLIP_PATH_TCGEN05 = 2 };
-enum { MCLIP_OP_ROW_LSE = 0, MCLIP_OP_BLOCK_GRAD = 1 };
+enum { MCLIP_OP_ROW_LSE = 0, MCLIP_OP_BLOCK_GRAD = 1, MCLIP_OP_PAIR_LSE = 2, MCLIP_OP_PAIR_REF = 3 };
 enum {
   MCLIP_OK = 0,
   MCLIP_ERR_INVALID = 1,      /* bad shape / pointer / alignment / enum */
@@ -61,10 +61,54 @@ int mclip_workspace_bytes(int64_t M, int64_t N, int64_t D, int dtype, int op, in
  * the log_softmax half of F.cross_entropy at loss.py:143-144; `diag_off` is the label offset of
  * loss.py:80-81 (`labels + num_logits * rank`).  Called twice per forward: (image rows, all text) and
  * (text rows, all image).  `logit_scale` is a device scalar (no host sync).  `diag` and `rowdot` may be NULL.
+ * `run_if` (device int, may be NULL): when non-NULL and *run_if == 0 at execution time, every kernel of the call
+ * exits immediately and no output is written -- this is how the robust one-sided path is chained behind
+ * mclip_pair_lse's status flag without a host synchronisation.  A predicated call must pass diag == NULL.
  */
 int mclip_row_lse(const void* X, const void* Y, int64_t M, int64_t N, int64_t D, int64_t ldx, int64_t ldy,
                   int dtype, const float* logit_scale, int64_t diag_off, float* lse, float* diag, float* rowdot,
-                  void* ws, size_t ws_bytes, int path, void* cuda_stream);
+                  const int* run_if, void* ws, size_t ws_bytes, int path, void* cuda_stream);
+
+/*
+ * Two-sided forward: one pass over S = logit_scale * X @ Y^T produces BOTH directions of the loss
+ * (reference loss.py:102-111 builds logits_per_image and logits_per_text, :142-145 runs cross_entropy on each):
+ *   row_lse[i] = log sum_j exp(S[i, j])                     rowdot[i] = sum_j softmax_j(S[i, :]) <X[i], Y[j]>
+ *   col_out[j] = log sum_i exp(S[i, j])  (col_mode 0)   or   sum_i 2^(S[i, j] log2(e) - ref[0])  (col_mode 1)
+ * All exponentials use the single reference ref[0] (log2 units) produced by mclip_pair_ref, so partial column sums
+ * of different row blocks simply add.  In col_mode 1 (row block of one rank, M < all rows) col_out has N + 2 slots:
+ * the raw sums, then ref[0], then the status word; all-gather these vectors and finish the rank's own columns with
+ * mclip_merge_col_sums (or a single vector with mclip_lse_from_sum).  Validity is checked on the result: if any row / column total leaves
+ * [2^-75, 2^120] the call ORs a non-zero bit into *status (device int) and the outputs must be recomputed by
+ * mclip_row_lse(..., run_if = status).  tcgen05 path only: mclip_pair_supported() says whether a problem qualifies
+ * (bf16/f16, D % 8 == 0, D <= 512, leading dimensions % 8 == 0).
+ */
+int mclip_pair_supported(int64_t M, int64_t N, int64_t D, int64_t ldx, int64_t ldy, int dtype);
+
+/*
+ * diag[i] = <X[i], Y[i + diag_off]> (raw dot, 0 when the index is outside [0, N)) -- the positive-pair logits the
+ * loss needs anyway (labels of loss.py:76-87) -- and ref[0] = max_i(logit_scale log2(e) diag[i]) - 40, the uniform
+ * exponent reference of mclip_pair_lse.  Also zeroes *status (may be NULL).  Workspace: MCLIP_OP_PAIR_REF.
+ */
+int mclip_pair_ref(const void* X, const void* Y, int64_t M, int64_t N, int64_t D, int64_t ldx, int64_t ldy, int dtype,
+                   const float* logit_scale, int64_t diag_off, float* diag, float* ref, int* status, void* ws,
+                   size_t ws_bytes, void* cuda_stream);
+
+int mclip_pair_lse(const void* X, const void* Y, int64_t M, int64_t N, int64_t D, int64_t ldx, int64_t ldy, int dtype,
+                   const float* logit_scale, const float* ref, float* row_lse, float* rowdot, float* col_out,
+                   int col_mode, int* status, void* ws, size_t ws_bytes, void* cuda_stream);
+
+/*
+ * Column LSEs of columns [col0, col0 + n) from W gathered col_mode-1 vectors (`parts`, W rows of `stride` >= n_total + 2
+ * floats, n_total = N of the producing calls): lse[j] = ln2 * (m + log2(sum_q parts[q][col0 + j] 2^(ref_q - m))),
+ * m = max_q ref_q.  ORs every producer's status word, and 2 for an out-of-window total, into *status.
+ * This is the only cross-rank step of the text->image direction: it replaces the second logits block of
+ * loss.py:102-111 at W > 1.
+ */
+int mclip_merge_col_sums(const float* parts, int W, int64_t stride, int64_t n_total, int64_t col0, int64_t n, float* lse,
+                         int* status, void* cuda_stream);
+
+/* lse[i] = ln(2) * (ref[0] + log2(sum[i])); ORs 2 into *status if a sum is outside [2^-75, 2^120]. */
+int mclip_lse_from_sum(const float* sum, int64_t n, const float* ref, float* lse, int* status, void* cuda_stream);
 
 /*
  * Gradient of one logits block w.r.t. its row operand, recomputing the block (never stored):

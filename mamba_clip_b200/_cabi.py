@@ -15,10 +15,10 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmclip_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 DTYPE_CODES = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
 PATH_AUTO, PATH_SIMT, PATH_TCGEN05 = 0, 1, 2
-OP_ROW_LSE, OP_BLOCK_GRAD = 0, 1
+OP_ROW_LSE, OP_BLOCK_GRAD, OP_PAIR_LSE, OP_PAIR_REF = 0, 1, 2, 3
 
 _c_f32p = ctypes.c_void_p
 _SIGNATURES = {
@@ -29,8 +29,18 @@ _SIGNATURES = {
     "mclip_select_path": (ctypes.c_int, [ctypes.c_int64] * 5 + [ctypes.c_int, ctypes.c_int]),
     "mclip_workspace_bytes": (ctypes.c_int, [ctypes.c_int64] * 3 + [ctypes.c_int] * 3 + [ctypes.POINTER(ctypes.c_size_t)]),
     "mclip_row_lse": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int64] * 5 + [ctypes.c_int, _c_f32p,
-                                     ctypes.c_int64, _c_f32p, _c_f32p, _c_f32p, ctypes.c_void_p, ctypes.c_size_t,
-                                     ctypes.c_int, ctypes.c_void_p]),
+                                     ctypes.c_int64, _c_f32p, _c_f32p, _c_f32p, ctypes.c_void_p, ctypes.c_void_p,
+                                     ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]),
+    "mclip_pair_supported": (ctypes.c_int, [ctypes.c_int64] * 5 + [ctypes.c_int]),
+    "mclip_pair_ref": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int64] * 5 + [ctypes.c_int, _c_f32p,
+                                      ctypes.c_int64, _c_f32p, _c_f32p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                      ctypes.c_void_p]),
+    "mclip_pair_lse": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int64] * 5 + [ctypes.c_int, _c_f32p,
+                                      _c_f32p, _c_f32p, _c_f32p, _c_f32p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                      ctypes.c_size_t, ctypes.c_void_p]),
+    "mclip_merge_col_sums": (ctypes.c_int, [_c_f32p, ctypes.c_int] + [ctypes.c_int64] * 4 + [_c_f32p, ctypes.c_void_p,
+                                            ctypes.c_void_p]),
+    "mclip_lse_from_sum": (ctypes.c_int, [_c_f32p, ctypes.c_int64, _c_f32p, _c_f32p, ctypes.c_void_p, ctypes.c_void_p]),
     "mclip_block_grad": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int64] * 5 + [ctypes.c_int, _c_f32p,
                                         _c_f32p, _c_f32p, _c_f32p, ctypes.c_int64] + [ctypes.c_float] * 4 +
                          [ctypes.c_void_p, ctypes.c_int64, _c_f32p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
@@ -147,24 +157,90 @@ class CudaBackend:
 
     # -- ops -------------------------------------------------------------------------------------
     def row_lse(self, X: torch.Tensor, Y: torch.Tensor, ls: torch.Tensor, diag_off: int, want_diag: bool,
-                want_rowdot: bool = False):
-        """-> (lse, diag or None) or, with want_rowdot, (lse, diag or None, rowdot)."""
+                want_rowdot: bool = False, run_if: Optional[torch.Tensor] = None, out_lse: Optional[torch.Tensor] = None,
+                out_rowdot: Optional[torch.Tensor] = None):
+        """-> (lse, diag or None) or, with want_rowdot, (lse, diag or None, rowdot).
+        `run_if` (device int32 scalar): the launches exit without writing when it is 0 at execution time; such a
+        call writes into the caller's `out_lse` / `out_rowdot` and cannot produce `diag`."""
         dev = self._prep(X, Y, ls)
         M, D = X.shape
         N = Y.shape[0]
-        nout = 1 + int(want_diag) + int(want_rowdot)
-        out = torch.empty((nout, M), dtype=torch.float32, device=dev)
-        lse = out[0]
-        diag = out[1] if want_diag else None
-        rowdot = out[nout - 1] if want_rowdot else None
+        if run_if is not None:
+            if want_diag or out_lse is None or (want_rowdot and out_rowdot is None):
+                raise ValueError("a predicated row_lse needs caller-provided outputs and cannot write diag")
+            lse, diag, rowdot = out_lse, None, (out_rowdot if want_rowdot else None)
+        else:
+            nout = 1 + int(want_diag) + int(want_rowdot)
+            out = torch.empty((nout, M), dtype=torch.float32, device=dev)
+            lse = out[0]
+            diag = out[1] if want_diag else None
+            rowdot = out[nout - 1] if want_rowdot else None
         stream = torch.cuda.current_stream(dev).cuda_stream
         ws, nws = self._workspace(M, N, D, X.dtype, OP_ROW_LSE, dev, stream)
         with self._DeviceGuard(dev):
             rc = self.lib.mclip_row_lse(_ptr(X), _ptr(Y), M, N, D, X.stride(0), Y.stride(0), DTYPE_CODES[X.dtype],
-                                        _ptr(ls), diag_off, _ptr(lse), _ptr(diag), _ptr(rowdot), _ptr(ws), nws,
-                                        self.path, ctypes.c_void_p(stream))
+                                        _ptr(ls), diag_off, _ptr(lse), _ptr(diag), _ptr(rowdot), _ptr(run_if), _ptr(ws),
+                                        nws, self.path, ctypes.c_void_p(stream))
         _check(self.lib, rc, "mclip_row_lse")
         return (lse, diag, rowdot) if want_rowdot else (lse, diag)
+
+    def pair_supported(self, X: torch.Tensor, Y: torch.Tensor) -> bool:
+        """True when the two-sided forward (one pass for both loss directions) can run this problem."""
+        if self.path == PATH_SIMT or X.dtype not in DTYPE_CODES or os.environ.get("MCLIP_NO_PAIR_FWD") == "1":
+            return False
+        return bool(self.lib.mclip_pair_supported(X.shape[0], Y.shape[0], X.shape[1], X.stride(0), Y.stride(0),
+                                                  DTYPE_CODES[X.dtype]))
+
+    def pair_ref(self, X, Y, ls, diag_off):
+        """-> (diag [M], ref [1], status [1] int32 zeroed): positive-pair dots and the uniform exponent reference."""
+        dev = self._prep(X, Y, ls)
+        M, D = X.shape
+        N = Y.shape[0]
+        out = torch.empty(M + 2, dtype=torch.float32, device=dev)
+        diag, ref, status = out[:M], out[M:M + 1], out[M + 1:M + 2].view(torch.int32)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        ws, nws = self._workspace(M, N, D, X.dtype, OP_PAIR_REF, dev, stream)
+        with self._DeviceGuard(dev):
+            rc = self.lib.mclip_pair_ref(_ptr(X), _ptr(Y), M, N, D, X.stride(0), Y.stride(0), DTYPE_CODES[X.dtype], _ptr(ls),
+                                         diag_off, _ptr(diag), _ptr(ref), _ptr(status), _ptr(ws), nws, ctypes.c_void_p(stream))
+        _check(self.lib, rc, "mclip_pair_ref")
+        return diag, ref, status
+
+    def pair_lse(self, X, Y, ls, ref, status, want_rowdot: bool, col_mode: int = 0):
+        """-> (row_lse [M], rowdot [M] or None, col_out [N]); ORs into `status` when the result is unusable."""
+        dev = self._prep(X, Y, ls, ref, status)
+        M, D = X.shape
+        N = Y.shape[0]
+        rows = torch.empty((2, M), dtype=torch.float32, device=dev)
+        col_out = torch.empty(N + (2 if col_mode == 1 else 0), dtype=torch.float32, device=dev)
+        row_lse, rowdot = rows[0], (rows[1] if want_rowdot else None)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        ws, nws = self._workspace(M, N, D, X.dtype, OP_PAIR_LSE, dev, stream)
+        with self._DeviceGuard(dev):
+            rc = self.lib.mclip_pair_lse(_ptr(X), _ptr(Y), M, N, D, X.stride(0), Y.stride(0), DTYPE_CODES[X.dtype], _ptr(ls),
+                                         _ptr(ref), _ptr(row_lse), _ptr(rowdot), _ptr(col_out), col_mode, _ptr(status),
+                                         _ptr(ws), nws, ctypes.c_void_p(stream))
+        _check(self.lib, rc, "mclip_pair_lse")
+        return row_lse, rowdot, col_out
+
+    def merge_col_sums(self, parts, n_total, col0, n, status):
+        """parts: [W, n_total + 2] gathered col_mode-1 vectors -> column LSEs of columns [col0, col0 + n)."""
+        dev = self._prep(parts, status)
+        lse = torch.empty(n, dtype=torch.float32, device=dev)
+        with self._DeviceGuard(dev):
+            rc = self.lib.mclip_merge_col_sums(_ptr(parts), parts.shape[0], parts.stride(0), n_total, col0, n, _ptr(lse),
+                                               _ptr(status), ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        _check(self.lib, rc, "mclip_merge_col_sums")
+        return lse
+
+    def lse_from_sum(self, sums, ref, status):
+        dev = self._prep(sums, ref, status)
+        lse = torch.empty_like(sums)
+        with self._DeviceGuard(dev):
+            rc = self.lib.mclip_lse_from_sum(_ptr(sums), sums.numel(), _ptr(ref), _ptr(lse), _ptr(status),
+                                             ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        _check(self.lib, rc, "mclip_lse_from_sum")
+        return lse
 
     def block_grad(self, X, Y, ls, go, lse_x, lse_y, diag_off, w_row, w_col, w_diag, inv_2n, want_rowdot=True):
         dev = self._prep(X, Y, ls, lse_x)

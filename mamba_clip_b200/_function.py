@@ -81,12 +81,30 @@ class ClipLossFunction(torch.autograd.Function):
 
         # u, v: softmax-weighted raw dots (sum_j P_ij <x_i, y_j>) of the two blocks -- all d(logit_scale) needs
         need_ls = torch.is_tensor(logit_scale) and logit_scale.requires_grad
-        r1 = be.row_lse(xi, all_t, ls, off, True, need_ls)       # rows R of S
-        if work_i is not None:
-            work_i.wait()
-        r2 = be.row_lse(xt, all_i, ls, off, False, need_ls)      # columns R of S
-        row_lse, diag, col_lse = r1[0], r1[1], r2[0]
-        ctx.uv = (r1[2], r2[2]) if need_ls else None
+        if getattr(be, "pair_supported", lambda *_: False)(xi, all_t):
+            # two-sided forward: one pass over the rank's row block S_r = ls * I_r T_all^T gives its row LSEs and the
+            # sums of every column over its rows (1 GEMM unit instead of 2).  At W > 1 the per-rank column sums are
+            # all-gathered (4 * (B_g + 2) bytes per rank) and each rank finishes its own columns.  The result is
+            # validated on the device; the predicated one-sided calls behind it redo the work with running maxima
+            # when the status flag was raised (they exit at once otherwise -- no host sync).
+            diag, ref, status = be.pair_ref(xi, all_t, ls, off)
+            if W == 1:
+                row_lse, u, col_lse = be.pair_lse(xi, all_t, ls, ref, status, need_ls)
+            else:
+                row_lse, u, col_part = be.pair_lse(xi, all_t, ls, ref, status, need_ls, col_mode=1)
+                parts = _gather_rows(col_part.unsqueeze(0), W, group)           # [W, B_g + 2]
+                col_lse = be.merge_col_sums(parts, W * Bl, off, Bl, status)
+                work_i.wait()
+            be.row_lse(xi, all_t, ls, off, False, need_ls, run_if=status, out_lse=row_lse, out_rowdot=u)
+            be.row_lse(xt, all_i, ls, off, False, False, run_if=status, out_lse=col_lse)
+            ctx.uv = (u, None) if need_ls else None   # v comes out of the text-side backward kernel
+        else:
+            r1 = be.row_lse(xi, all_t, ls, off, True, need_ls)       # rows R of S
+            if work_i is not None:
+                work_i.wait()
+            r2 = be.row_lse(xt, all_i, ls, off, False, need_ls)      # columns R of S
+            row_lse, diag, col_lse = r1[0], r1[1], r2[0]
+            ctx.uv = (r1[2], r2[2]) if need_ls else None
         loss = be.loss_finalize(row_lse, col_lse, diag, ls)      # the rank's local loss
         if W > 1 and not local_loss:
             # reference: one global [B_g, B_g] problem on every rank == mean of the equal-sized rank losses
@@ -139,13 +157,21 @@ class ClipLossFunction(torch.autograd.Function):
             lse_y_i, lse_y_t = col_lse_all, row_lse_all
 
         need_i, need_t, need_ls = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
-        d_img = d_txt = d_ls = None
+        need_ls = need_ls and ctx.ls_meta is not None and ctx.uv is not None
+        # after a two-sided forward the text-side softmax-weighted dots v are still missing: the text-side
+        # backward kernel emits them as its `rowdot`
+        want_v = need_ls and ctx.uv[1] is None
+        d_img = d_txt = d_ls = v_bwd = None
         if need_i:
             d_img, _ = be.block_grad(xi, all_t, ls, go, row_lse, lse_y_i, off, w_row, w_col, w_diag, inv_2n, False)
         if need_t:
-            d_txt, _ = be.block_grad(xt, all_i, ls, go, col_lse, lse_y_t, off, w_row, w_col, w_diag, inv_2n, False)
-        if need_ls and ctx.ls_meta is not None and ctx.uv is not None:
+            d_txt, v_bwd = be.block_grad(xt, all_i, ls, go, col_lse, lse_y_t, off, w_row, w_col, w_diag, inv_2n, want_v)
+        elif want_v:
+            v_bwd = be.row_lse(xt, all_i, ls, off, False, True)[2]
+        if need_ls:
             u, v = ctx.uv
+            if v is None:
+                v = v_bwd
             n_ls = Bl if (W > 1 and local_loss) else Bg
             t, d_ls = be.dls_finalize(u, v, diag, go, 1.0 / (2.0 * n_ls))
             if W > 1 and not local_loss:

@@ -82,6 +82,8 @@ int mclip_workspace_bytes(int64_t M, int64_t N, int64_t D, int dtype, int op, in
   size_t simt = 0, tc = 0;
   if (op == MCLIP_OP_ROW_LSE) { simt = simt_row_lse_ws(M, N, D); tc = tc_row_lse_ws(M, N, D); }
   else if (op == MCLIP_OP_BLOCK_GRAD) { simt = simt_block_grad_ws(M, N, D); tc = tc_block_grad_ws(M, N, D); }
+  else if (op == MCLIP_OP_PAIR_LSE) { *bytes = tc_pair_lse_ws(M, N, D); return MCLIP_OK; }
+  else if (op == MCLIP_OP_PAIR_REF) { *bytes = pair_ref_ws(); return MCLIP_OK; }
   else { set_error("workspace_bytes: bad op %d", op); return MCLIP_ERR_INVALID; }
   if (path == MCLIP_PATH_SIMT) *bytes = simt;
   else if (path == MCLIP_PATH_TCGEN05) *bytes = tc;
@@ -91,7 +93,7 @@ int mclip_workspace_bytes(int64_t M, int64_t N, int64_t D, int dtype, int op, in
 
 int mclip_row_lse(const void* X, const void* Y, int64_t M, int64_t N, int64_t D, int64_t ldx, int64_t ldy,
                   int dtype, const float* logit_scale, int64_t diag_off, float* lse, float* diag, float* rowdot,
-                  void* ws, size_t ws_bytes, int path, void* cuda_stream) {
+                  const int* run_if, void* ws, size_t ws_bytes, int path, void* cuda_stream) {
   int rc = check_common(X, Y, M, N, D, ldx, ldy, dtype, logit_scale, path, "row_lse");
   if (rc) return rc;
   if (!lse) { set_error("row_lse: lse is null"); return MCLIP_ERR_INVALID; }
@@ -100,8 +102,56 @@ int mclip_row_lse(const void* X, const void* Y, int64_t M, int64_t N, int64_t D,
   if (rc) return rc;
   const size_t need = (p == MCLIP_PATH_TCGEN05) ? tc_row_lse_ws(M, N, D) : simt_row_lse_ws(M, N, D);
   if (need > 0 && (!ws || ws_bytes < need)) { set_error("row_lse: workspace %zu < %zu bytes", ws_bytes, need); return MCLIP_ERR_WORKSPACE; }
-  RowLseArgs a{X, Y, M, N, D, ldx, ldy, dtype, logit_scale, diag_off, lse, diag, rowdot, ws, ws_bytes, (cudaStream_t)cuda_stream};
+  if (run_if && diag) { set_error("row_lse: a predicated call (run_if) cannot write diag"); return MCLIP_ERR_INVALID; }
+  RowLseArgs a{X, Y, M, N, D, ldx, ldy, dtype, logit_scale, diag_off, lse, diag, rowdot, ws, ws_bytes, (cudaStream_t)cuda_stream, run_if};
   return (p == MCLIP_PATH_TCGEN05) ? tc_row_lse(a) : simt_row_lse(a);
+}
+
+int mclip_pair_supported(int64_t M, int64_t N, int64_t D, int64_t ldx, int64_t ldy, int dtype) {
+  return (M > 0 && N > 0 && D > 0 && tc_pair_supported(M, N, D, ldx, ldy, dtype)) ? 1 : 0;
+}
+
+int mclip_pair_ref(const void* X, const void* Y, int64_t M, int64_t N, int64_t D, int64_t ldx, int64_t ldy, int dtype,
+                   const float* logit_scale, int64_t diag_off, float* diag, float* ref, int* status, void* ws,
+                   size_t ws_bytes, void* cuda_stream) {
+  int rc = check_common(X, Y, M, N, D, ldx, ldy, dtype, logit_scale, MCLIP_PATH_AUTO, "pair_ref");
+  if (rc) return rc;
+  if (!diag || !ref) { set_error("pair_ref: null diag/ref"); return MCLIP_ERR_INVALID; }
+  if (!ws || ws_bytes < pair_ref_ws()) { set_error("pair_ref: workspace %zu < %zu bytes", ws_bytes, pair_ref_ws()); return MCLIP_ERR_WORKSPACE; }
+  PairRefArgs a{X, Y, M, N, D, ldx, ldy, dtype, logit_scale, diag_off, diag, ref, status, ws, (cudaStream_t)cuda_stream};
+  return launch_pair_ref(a);
+}
+
+int mclip_pair_lse(const void* X, const void* Y, int64_t M, int64_t N, int64_t D, int64_t ldx, int64_t ldy, int dtype,
+                   const float* logit_scale, const float* ref, float* row_lse, float* rowdot, float* col_out,
+                   int col_mode, int* status, void* ws, size_t ws_bytes, void* cuda_stream) {
+  int rc = check_common(X, Y, M, N, D, ldx, ldy, dtype, logit_scale, MCLIP_PATH_TCGEN05, "pair_lse");
+  if (rc) return rc;
+  if (!ref || !row_lse || !col_out || !status) { set_error("pair_lse: null ref/row_lse/col_out/status"); return MCLIP_ERR_INVALID; }
+  if (col_mode != 0 && col_mode != 1) { set_error("pair_lse: bad col_mode %d", col_mode); return MCLIP_ERR_INVALID; }
+  if (!tc_pair_supported(M, N, D, ldx, ldy, dtype)) {
+    set_error("pair_lse: needs bf16/f16, D %% 8 == 0, D <= 512, ld %% 8 == 0");
+    return MCLIP_ERR_UNSUPPORTED;
+  }
+  const size_t need = tc_pair_lse_ws(M, N, D);
+  if (!ws || ws_bytes < need) { set_error("pair_lse: workspace %zu < %zu bytes", ws_bytes, need); return MCLIP_ERR_WORKSPACE; }
+  PairLseArgs a{X, Y, M, N, D, ldx, ldy, dtype, logit_scale, ref, row_lse, rowdot, col_out, col_mode, status, ws, ws_bytes,
+                (cudaStream_t)cuda_stream};
+  return tc_pair_lse(a);
+}
+
+int mclip_merge_col_sums(const float* parts, int W, int64_t stride, int64_t n_total, int64_t col0, int64_t n, float* lse,
+                         int* status, void* cuda_stream) {
+  if (!parts || !lse || !status || W <= 0 || n <= 0 || col0 < 0 || col0 + n > n_total || stride < n_total + 2) {
+    set_error("merge_col_sums: invalid argument");
+    return MCLIP_ERR_INVALID;
+  }
+  return launch_merge_col_sums(parts, W, stride, n_total, col0, n, lse, status, (cudaStream_t)cuda_stream);
+}
+
+int mclip_lse_from_sum(const float* sum, int64_t n, const float* ref, float* lse, int* status, void* cuda_stream) {
+  if (!sum || !ref || !lse || !status || n <= 0) { set_error("lse_from_sum: invalid argument"); return MCLIP_ERR_INVALID; }
+  return launch_lse_from_sum(sum, n, ref, lse, status, (cudaStream_t)cuda_stream);
 }
 
 int mclip_block_grad(const void* X, const void* Y, int64_t M, int64_t N, int64_t D, int64_t ldx, int64_t ldy,

@@ -40,6 +40,36 @@ struct RowLseArgs {
   float* rowdot;     // may be null
   void* ws; size_t ws_bytes;
   cudaStream_t stream;
+  const int* run_if = nullptr;   // device flag: when non-null and *run_if == 0 every launch of the call exits at once
+};
+
+// two-sided forward (tc_pair_lse.cu)
+struct PairRefArgs {
+  const void* X; const void* Y;
+  int64_t M, N, D, ldx, ldy;
+  int dtype;
+  const float* logit_scale;
+  int64_t diag_off;
+  float* diag;       // [M] raw positive-pair dots
+  float* ref;        // [1] uniform exponent reference c0 (log2 units)
+  int* status;       // [1] zeroed here; may be null
+  void* ws;
+  cudaStream_t stream;
+};
+
+struct PairLseArgs {
+  const void* X; const void* Y;
+  int64_t M, N, D, ldx, ldy;
+  int dtype;
+  const float* logit_scale;
+  const float* ref;
+  float* row_lse;
+  float* rowdot;     // may be null
+  float* col_out;    // [N] column lse (col_mode 0) or [N + 2] raw column sums relative to ref, ref, status (col_mode 1)
+  int col_mode;
+  int* status;
+  void* ws; size_t ws_bytes;
+  cudaStream_t stream;
 };
 
 struct BlockGradArgs {
@@ -71,10 +101,20 @@ int tc_row_lse(const RowLseArgs& a);
 size_t tc_block_grad_ws(int64_t M, int64_t N, int64_t D);
 int tc_block_grad(const BlockGradArgs& a);
 
+// two-sided forward -- tc_pair_lse.cu
+bool tc_pair_supported(int64_t M, int64_t N, int64_t D, int64_t ldx, int64_t ldy, int dtype);
+size_t tc_pair_lse_ws(int64_t M, int64_t N, int64_t D);
+size_t pair_ref_ws();
+int launch_pair_ref(const PairRefArgs& a);
+int tc_pair_lse(const PairLseArgs& a);
+int launch_lse_from_sum(const float* sum, int64_t n, const float* ref, float* lse, int* status, cudaStream_t stream);
+int launch_merge_col_sums(const float* parts, int W, int64_t stride, int64_t n_total, int64_t col0, int64_t n, float* lse,
+                          int* status, cudaStream_t stream);
+
 // shared small kernels -- simt_kernels.cu
 // merge `nsplit` partial (max2, sum, sum*c) triples per row into a natural-log LSE (+ rowdot if asked for).
 int launch_lse_merge(const float* part_m2, const float* part_s, const float* part_c, int nsplit, int64_t M, float* lse,
-                     float* rowdot, cudaStream_t stream);
+                     float* rowdot, cudaStream_t stream, const int* run_if = nullptr);
 int launch_loss_finalize(const float* row_lse, const float* col_lse, const float* diag, int64_t n,
                          const float* logit_scale, float* loss, cudaStream_t stream);
 int launch_dls_finalize(const float* u, const float* v, const float* diag, int64_t n, const float* grad_out,

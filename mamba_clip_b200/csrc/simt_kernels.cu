@@ -123,7 +123,8 @@ simt_row_lse_kernel(const T* __restrict__ X, const T* __restrict__ Y, int64_t M,
 // ---------------------------------------------------------------------------------------------
 __global__ void lse_merge_kernel(const float* __restrict__ part_m2, const float* __restrict__ part_s,
                                  const float* __restrict__ part_c, int nsplit, int64_t M, float* __restrict__ lse,
-                                 float* __restrict__ rowdot) {
+                                 float* __restrict__ rowdot, const int* __restrict__ run_if) {
+  if (run_if != nullptr && *run_if == 0) return;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M) return;
   float m = -INFINITY;
@@ -320,7 +321,7 @@ int run_row_lse(const RowLseArgs& a) {
       a.logit_scale, a.diag_off, cols_per_split, part_m2, part_s, part_c, a.diag);
   count_launch();
   MCLIP_CUDA_OK(cudaGetLastError());
-  return launch_lse_merge(part_m2, part_s, part_c, real_splits, a.M, a.lse, a.rowdot, a.stream);
+  return launch_lse_merge(part_m2, part_s, part_c, real_splits, a.M, a.lse, a.rowdot, a.stream, a.run_if);
 }
 
 template <typename T>
@@ -364,8 +365,8 @@ int simt_block_grad(const BlockGradArgs& a) {
 }
 
 int launch_lse_merge(const float* part_m2, const float* part_s, const float* part_c, int nsplit, int64_t M, float* lse,
-                     float* rowdot, cudaStream_t stream) {
-  lse_merge_kernel<<<(unsigned)ceil_div(M, 256), 256, 0, stream>>>(part_m2, part_s, part_c, nsplit, M, lse, rowdot);
+                     float* rowdot, cudaStream_t stream, const int* run_if) {
+  lse_merge_kernel<<<(unsigned)ceil_div(M, 256), 256, 0, stream>>>(part_m2, part_s, part_c, nsplit, M, lse, rowdot, run_if);
   count_launch();
   MCLIP_CUDA_OK(cudaGetLastError());
   return MCLIP_OK;

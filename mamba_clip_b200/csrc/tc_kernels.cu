@@ -17,6 +17,7 @@
 
 #include "common.cuh"
 #include "sm100_ptx.cuh"
+#include "tc_host.cuh"
 
 namespace mclip {
 
@@ -57,6 +58,7 @@ struct FwdParams {
   float* diag;
   int bf16;
   int dbg;            // development switch (MCLIP_DBG & 16): print barrier-wait cycle counts of a few CTAs
+  const int* run_if;  // device flag (null = always run): 0 makes the whole grid exit before touching anything
 };
 
 struct BwdParams {
@@ -120,6 +122,7 @@ template <int BN, bool XRES>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_row_lse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
+  if (p.run_if != nullptr && *p.run_if == 0) return;
   const uint32_t smem_base = align1024(smem_u32(smem_raw));
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   constexpr uint32_t kYStage = BN * 128;
@@ -301,6 +304,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 tc_row_lse2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   constexpr int BN = 256;
+  if (p.run_if != nullptr && *p.run_if == 0) return;   // uniform over the grid: no CTA reaches the cluster barrier
   const uint32_t smem_base = align1024(smem_u32(smem_raw));
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t x_bytes = 8 * kChunkBytes;                       // [8][128 rows][64 k]
@@ -2138,6 +2142,12 @@ int set_smem(K kernel, uint32_t bytes) {
 
 }  // namespace
 
+int tc_make_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t D, int64_t ld, int dtype, uint32_t box_rows) {
+  return make_tmap(map, base, rows, D, ld, dtype, box_rows);
+}
+
+int tc_set_smem(const void* kernel, uint32_t bytes) { return set_smem(kernel, bytes); }
+
 bool tc_supported(int64_t M, int64_t N, int64_t D, int64_t ldx, int64_t ldy, int dtype, int op) {
   (void)M; (void)N; (void)op;
   if (dtype != MCLIP_DTYPE_BF16 && dtype != MCLIP_DTYPE_F16) return false;
@@ -2183,6 +2193,8 @@ int tc_row_lse(const RowLseArgs& a) {
   p.part_s = p.part_m2 + (size_t)f.nsplit * a.M;
   p.part_c = a.rowdot ? p.part_s + (size_t)f.nsplit * a.M : nullptr;
   p.diag = a.diag; p.bf16 = a.dtype == MCLIP_DTYPE_BF16;
+  p.run_if = a.run_if;
+  if (a.run_if && a.diag) { set_error("row_lse(tcgen05): a predicated call cannot write diag"); return MCLIP_ERR_INVALID; }
   {
     const char* e = getenv("MCLIP_DBG");
     p.dbg = e ? atoi(e) : 0;
@@ -2216,7 +2228,7 @@ int tc_row_lse(const RowLseArgs& a) {
   }
   count_launch();
   MCLIP_CUDA_OK(cudaGetLastError());
-  return launch_lse_merge(p.part_m2, p.part_s, p.part_c, f.nsplit, a.M, a.lse, a.rowdot, a.stream);
+  return launch_lse_merge(p.part_m2, p.part_s, p.part_c, f.nsplit, a.M, a.lse, a.rowdot, a.stream, a.run_if);
 }
 
 // transposed CTA-pair backward (D <= 512, no rowdot output)

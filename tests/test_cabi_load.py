@@ -47,7 +47,7 @@ def test_argument_validation_without_gpu(lib):
     assert lib.mclip_workspace_bytes(128, 128, 64, 7, 0, 0, ctypes.byref(n)) == 1
     assert b"invalid" in lib.mclip_last_error()
     # null pointers -> MCLIP_ERR_INVALID before any CUDA call
-    rc = lib.mclip_row_lse(None, None, 4, 4, 8, 8, 8, 0, None, 0, None, None, None, None, 0, 0, None)
+    rc = lib.mclip_row_lse(None, None, 4, 4, 8, 8, 8, 0, None, 0, None, None, None, None, None, 0, 0, None)
     assert rc == 1 and b"null" in lib.mclip_last_error()
     rc = lib.mclip_block_grad(None, None, 4, 4, 8, 8, 8, 0, None, None, None, None, 0, 1.0, 1.0, 2.0, 0.5,
                               None, 8, None, None, 0, 0, None)

@@ -30,6 +30,16 @@ def _free_port():
     return p
 
 
+def _features(W, job):
+    dtype = getattr(torch, job["dtype"])
+    img, txt = O.make_features(W * job["Bl"], job["D"], seed=job["seed"], correlated=job["corr"])
+    if job.get("adv"):
+        # the first half of the global batch has every logit ~ls nats below the other half's positives: the two-sided
+        # forward of the ranks owning those rows leaves its f32 window, which must switch ALL ranks to the robust path
+        img[: W * job["Bl"] // 2] *= 0.01
+    return img.to(dtype), txt.to(dtype)
+
+
 def _worker(rank, W, port, jobs, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -41,7 +51,7 @@ def _worker(rank, W, port, jobs, q):
         for j, job in enumerate(jobs):
             Bl, D = job["Bl"], job["D"]
             dtype = getattr(torch, job["dtype"])
-            img, txt = O.make_features(W * Bl, D, seed=job["seed"], correlated=job["corr"], dtype=dtype)
+            img, txt = _features(W, job)
             a = img[rank * Bl:(rank + 1) * Bl].to(dev).requires_grad_(True)
             b = txt[rank * Bl:(rank + 1) * Bl].to(dev).requires_grad_(True)
             ls = torch.tensor(job["ls"], device=dev, requires_grad=True)
@@ -99,10 +109,12 @@ def test_nccl_bf16_tensor_core_sizes_against_oracle(W):
         for gwg in (False, True):
             jobs.append(dict(Bl=256, D=512, dtype="bfloat16", seed=77, corr=True, ls=20.0, go=2.0,
                              local_loss=local_loss, gwg=gwg))
+    jobs.append(dict(Bl=256, D=512, dtype="bfloat16", seed=78, corr=True, ls=100.0, go=2.0, local_loss=True, gwg=True,
+                     adv=True))
     out = _run(W, jobs)
     for j, job in enumerate(jobs):
-        img, txt = O.make_features(W * 256, 512, seed=77, correlated=True, dtype=torch.bfloat16)
-        ref = O.ref_port_ranks(img.float(), txt.float(), 20.0, W, job["local_loss"], job["gwg"], grad_output=2.0)
+        img, txt = _features(W, job)
+        ref = O.ref_port_ranks(img.float(), txt.float(), job["ls"], W, job["local_loss"], job["gwg"], grad_output=2.0)
         for r in range(W):
             loss, di, dt, dls = out[(j, r)]
             assert abs(loss - float(ref[r].loss)) <= 2e-3 * abs(float(ref[r].loss)) + 1e-6

@@ -168,6 +168,119 @@ def test_block_grad_transposed_pair_kernel(M, N, D, ls, diag_off, w, monkeypatch
     assert float((dx.cpu().double() - ref_dx).norm()) <= 2e-3 * float(ref_dx.norm()) + 8 * 1.2e-7 * max(1.0, ls) * scale
 
 
+PAIR_CASES = [
+    # (dtype, M, N, D, ls, diag_off, correlated)
+    (torch.bfloat16, 64, 64, 64, 14.2857, 0, True),
+    (torch.bfloat16, 1, 1, 8, 5.0, 0, False),
+    (torch.bfloat16, 256, 256, 512, 14.2857, 0, True),
+    (torch.bfloat16, 129, 300, 512, 30.0, 64, True),
+    (torch.bfloat16, 300, 129, 200, 30.0, -20, False),
+    (torch.float16, 700, 1000, 256, 25.0, 17, True),
+    (torch.bfloat16, 2048, 2048, 512, 14.2857, 0, False),
+    (torch.bfloat16, 1000, 5000, 512, 40.0, 1024, True),
+    (torch.bfloat16, 384, 640, 128, -12.0, 0, True),     # negative scale
+    (torch.bfloat16, 4096, 4096, 512, 100.0, 0, True),   # saturated, all positives near the maximum
+]
+
+
+@pytest.mark.parametrize("dtype,M,N,D,ls,diag_off,corr", PAIR_CASES,
+                         ids=["-".join(str(v).split(".")[-1] for v in c) for c in PAIR_CASES])
+def test_pair_lse_two_sided_forward(dtype, M, N, D, ls, diag_off, corr):
+    """One pass over S yields row LSE + rowdot AND column LSE (mclip_pair_ref + mclip_pair_lse) == the oracle's
+    two one-sided statements; status stays 0 for these well-conditioned inputs; results are deterministic."""
+    be = backend(TC)
+    x, y = feats(M, N, D, dtype, seed=M * 5 + N, correlated=corr)
+    xd, yd = x.cuda(), y.cuda()
+    lsd = torch.tensor([ls], dtype=torch.float32, device="cuda")
+    assert be.pair_supported(xd, yd)
+    diag, ref, status = be.pair_ref(xd, yd, lsd, diag_off)
+    row_lse, rowdot, col_lse = be.pair_lse(xd, yd, lsd, ref, status, True)
+    torch.cuda.synchronize()
+    assert int(status.item()) == 0
+    ref_row, ref_diag = O.block_row_lse(x.float(), y.float(), ls, diag_off)
+    ref_col, _ = O.block_row_lse(y.float(), x.float(), ls, None)
+    tol = TOL[dtype] * max(1.0, abs(ls)) * 0.5 + 2e-6
+    assert float((diag.cpu().double() - ref_diag).abs().max()) <= 2e-6
+    assert float((row_lse.cpu().double() - ref_row).abs().max()) <= tol
+    assert float((col_lse.cpu().double() - ref_col).abs().max()) <= tol
+    C = x.double() @ y.double().T
+    ref_rd = (torch.exp(ls * C - ref_row[:, None]) * C).sum(dim=1)
+    assert float((rowdot.cpu().double() - ref_rd).abs().max()) <= 2e-3 * max(1.0, float(ref_rd.abs().max()))
+    # raw column sums (the multi-rank form): ln2 * (ref + log2(sum)) is the same column LSE
+    _, _, col_sum = be.pair_lse(xd, yd, lsd, ref, status, False, col_mode=1)
+    assert col_sum.numel() == N + 2 and float(col_sum[N]) == float(ref) and col_sum[N + 1:].view(torch.int32).item() == 0
+    col2 = be.lse_from_sum(col_sum[:N], ref, status)
+    row2, _, col3 = be.pair_lse(xd, yd, lsd, ref, status, False)
+    torch.cuda.synchronize()
+    assert torch.equal(col2, col_lse) and torch.equal(col3, col_lse) and torch.equal(row2, row_lse)
+    assert int(status.item()) == 0
+
+
+def test_pair_lse_flags_out_of_window_and_predicated_fallback_repairs():
+    """Logits spread over more than the f32 window (half of the rows have every logit ~100 nats below the largest
+    positive pair): the two-sided pass must raise the status flag, and the predicated one-sided calls chained behind
+    it must then produce the right LSEs.  With a clean status the same predicated calls must leave their outputs
+    untouched."""
+    be = backend(TC)
+    B, D, ls = 512, 128, 100.0
+    g = torch.Generator().manual_seed(5)
+    x = torch.nn.functional.normalize(torch.randn(B, D, generator=g), dim=-1)
+    y = x.clone()
+    x[: B // 2] *= 0.01                     # these rows: all logits within ~1 nat of 0; the others peak at ls = 100
+    x, y = x.bfloat16(), y.bfloat16()
+    xd, yd = x.cuda(), y.cuda()
+    lsd = torch.tensor([ls], dtype=torch.float32, device="cuda")
+    diag, ref, status = be.pair_ref(xd, yd, lsd, 0)
+    row_lse, rowdot, col_lse = be.pair_lse(xd, yd, lsd, ref, status, True)
+    assert int(status.item()) != 0
+    be.row_lse(xd, yd, lsd, 0, False, True, run_if=status, out_lse=row_lse, out_rowdot=rowdot)
+    be.row_lse(yd, xd, lsd, 0, False, False, run_if=status, out_lse=col_lse)
+    torch.cuda.synchronize()
+    ref_row, _ = O.block_row_lse(x.float(), y.float(), ls, 0)
+    ref_col, _ = O.block_row_lse(y.float(), x.float(), ls, None)
+    assert float((row_lse.cpu().double() - ref_row).abs().max()) <= 2e-3 * ls * 0.5
+    assert float((col_lse.cpu().double() - ref_col).abs().max()) <= 2e-3 * ls * 0.5
+    # clean status -> predicated calls are no-ops
+    status.zero_()
+    sentinel = torch.full_like(row_lse, -7.0)
+    be.row_lse(xd, yd, lsd, 0, False, False, run_if=status, out_lse=sentinel)
+    torch.cuda.synchronize()
+    assert bool((sentinel == -7.0).all())
+    # and the whole loss is right on such inputs
+    from mamba_clip_b200 import ClipLoss
+    a = xd.clone().requires_grad_(True)
+    b = yd.clone().requires_grad_(True)
+    s = torch.tensor(ls, device="cuda", requires_grad=True)
+    loss = ClipLoss()(a, b, s, output_dict=False)
+    loss.backward()
+    want = O.closed_form(x.float(), y.float(), ls, 1, 0, False, False)
+    assert abs(float(loss.detach()) - float(want.loss)) <= 2e-3 * abs(float(want.loss)) + 3e-6
+    assert abs(float(s.grad) - float(want.d_logit_scale)) <= 2e-3 * abs(float(want.d_logit_scale)) + 1e-4
+
+
+def test_pair_forward_matches_one_sided_forward_in_the_loss():
+    """ClipLoss through the two-sided forward == ClipLoss with it disabled (MCLIP_NO_PAIR_FWD=1), to f32 rounding."""
+    from mamba_clip_b200 import ClipLoss
+    img, txt = O.make_features(3000, 512, seed=3, correlated=True, dtype=torch.bfloat16)
+    outs = []
+    for flag in ("0", "1"):
+        os.environ["MCLIP_NO_PAIR_FWD"] = flag
+        try:
+            a = img.cuda().requires_grad_(True)
+            b = txt.cuda().requires_grad_(True)
+            s = torch.tensor(20.0, device="cuda", requires_grad=True)
+            loss = ClipLoss()(a, b, s, output_dict=False)
+            loss.backward()
+            outs.append((float(loss.detach()), a.grad.float().cpu(), b.grad.float().cpu(), float(s.grad)))
+        finally:
+            os.environ.pop("MCLIP_NO_PAIR_FWD", None)
+    (l0, di0, dt0, ds0), (l1, di1, dt1, ds1) = outs
+    assert abs(l0 - l1) <= 1e-5 * abs(l1)      # both are f32 sums of LSEs of magnitude ~ls
+    assert abs(ds0 - ds1) <= 1e-4 * abs(ds1) + 1e-8
+    assert float((di0 - di1).norm()) <= 1e-3 * float(di1.norm())
+    assert float((dt0 - dt1).norm()) <= 1e-3 * float(dt1.norm())
+
+
 def load_single():
     z = np.load(os.path.join(GOLD, "single.npz"))
     return z, json.loads(str(z["cases"]))
