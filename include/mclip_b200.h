@@ -81,6 +81,9 @@ int mclip_row_lse(const void* X, const void* Y, int64_t M, int64_t N, int64_t D,
  * [2^-75, 2^120] the call ORs a non-zero bit into *status (device int) and the outputs must be recomputed by
  * mclip_row_lse(..., run_if = status).  tcgen05 path only: mclip_pair_supported() says whether a problem qualifies
  * (bf16/f16, D % 8 == 0, D <= 512, leading dimensions % 8 == 0).
+ * `diag` (may be NULL; otherwise the vector mclip_pair_ref filled, same diag_off) is overwritten with the tensor-core
+ * accumulator's own <X[i], Y[i + diag_off]>: with a saturated softmax the loss subtracts logit_scale * diag from an LSE
+ * dominated by that same product, so both must carry identical rounding.
  */
 int mclip_pair_supported(int64_t M, int64_t N, int64_t D, int64_t ldx, int64_t ldy, int dtype);
 
@@ -94,8 +97,8 @@ int mclip_pair_ref(const void* X, const void* Y, int64_t M, int64_t N, int64_t D
                    size_t ws_bytes, void* cuda_stream);
 
 int mclip_pair_lse(const void* X, const void* Y, int64_t M, int64_t N, int64_t D, int64_t ldx, int64_t ldy, int dtype,
-                   const float* logit_scale, const float* ref, float* row_lse, float* rowdot, float* col_out,
-                   int col_mode, int* status, void* ws, size_t ws_bytes, void* cuda_stream);
+                   const float* logit_scale, const float* ref, int64_t diag_off, float* diag, float* row_lse, float* rowdot,
+                   float* col_out, int col_mode, int* status, void* ws, size_t ws_bytes, void* cuda_stream);
 
 /*
  * Column LSEs of columns [col0, col0 + n) from W gathered col_mode-1 vectors (`parts`, W rows of `stride` >= n_total + 2

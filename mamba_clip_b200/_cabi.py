@@ -36,7 +36,7 @@ _SIGNATURES = {
                                       ctypes.c_int64, _c_f32p, _c_f32p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
                                       ctypes.c_void_p]),
     "mclip_pair_lse": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int64] * 5 + [ctypes.c_int, _c_f32p,
-                                      _c_f32p, _c_f32p, _c_f32p, _c_f32p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                      _c_f32p, ctypes.c_int64, _c_f32p, _c_f32p, _c_f32p, _c_f32p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                       ctypes.c_size_t, ctypes.c_void_p]),
     "mclip_merge_col_sums": (ctypes.c_int, [_c_f32p, ctypes.c_int] + [ctypes.c_int64] * 4 + [_c_f32p, ctypes.c_void_p,
                                             ctypes.c_void_p]),
@@ -206,8 +206,9 @@ class CudaBackend:
         _check(self.lib, rc, "mclip_pair_ref")
         return diag, ref, status
 
-    def pair_lse(self, X, Y, ls, ref, status, want_rowdot: bool, col_mode: int = 0):
-        """-> (row_lse [M], rowdot [M] or None, col_out [N]); ORs into `status` when the result is unusable."""
+    def pair_lse(self, X, Y, ls, ref, status, want_rowdot: bool, col_mode: int = 0, diag=None, diag_off: int = 0):
+        """-> (row_lse [M], rowdot [M] or None, col_out [N]); ORs into `status` when the result is unusable.
+        `diag` (from pair_ref, same diag_off) is overwritten in place with the accumulator's own positive-pair dots."""
         dev = self._prep(X, Y, ls, ref, status)
         M, D = X.shape
         N = Y.shape[0]
@@ -218,7 +219,8 @@ class CudaBackend:
         ws, nws = self._workspace(M, N, D, X.dtype, OP_PAIR_LSE, dev, stream)
         with self._DeviceGuard(dev):
             rc = self.lib.mclip_pair_lse(_ptr(X), _ptr(Y), M, N, D, X.stride(0), Y.stride(0), DTYPE_CODES[X.dtype], _ptr(ls),
-                                         _ptr(ref), _ptr(row_lse), _ptr(rowdot), _ptr(col_out), col_mode, _ptr(status),
+                                         _ptr(ref), diag_off, _ptr(diag), _ptr(row_lse), _ptr(rowdot), _ptr(col_out),
+                                         col_mode, _ptr(status),
                                          _ptr(ws), nws, ctypes.c_void_p(stream))
         _check(self.lib, rc, "mclip_pair_lse")
         return row_lse, rowdot, col_out

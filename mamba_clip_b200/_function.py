@@ -89,9 +89,9 @@ class ClipLossFunction(torch.autograd.Function):
             # when the status flag was raised (they exit at once otherwise -- no host sync).
             diag, ref, status = be.pair_ref(xi, all_t, ls, off)
             if W == 1:
-                row_lse, u, col_lse = be.pair_lse(xi, all_t, ls, ref, status, need_ls)
+                row_lse, u, col_lse = be.pair_lse(xi, all_t, ls, ref, status, need_ls, diag=diag, diag_off=off)
             else:
-                row_lse, u, col_part = be.pair_lse(xi, all_t, ls, ref, status, need_ls, col_mode=1)
+                row_lse, u, col_part = be.pair_lse(xi, all_t, ls, ref, status, need_ls, col_mode=1, diag=diag, diag_off=off)
                 parts = _gather_rows(col_part.unsqueeze(0), W, group)           # [W, B_g + 2]
                 col_lse = be.merge_col_sums(parts, W * Bl, off, Bl, status)
                 work_i.wait()

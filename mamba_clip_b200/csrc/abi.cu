@@ -123,8 +123,8 @@ int mclip_pair_ref(const void* X, const void* Y, int64_t M, int64_t N, int64_t D
 }
 
 int mclip_pair_lse(const void* X, const void* Y, int64_t M, int64_t N, int64_t D, int64_t ldx, int64_t ldy, int dtype,
-                   const float* logit_scale, const float* ref, float* row_lse, float* rowdot, float* col_out,
-                   int col_mode, int* status, void* ws, size_t ws_bytes, void* cuda_stream) {
+                   const float* logit_scale, const float* ref, int64_t diag_off, float* diag, float* row_lse, float* rowdot,
+                   float* col_out, int col_mode, int* status, void* ws, size_t ws_bytes, void* cuda_stream) {
   int rc = check_common(X, Y, M, N, D, ldx, ldy, dtype, logit_scale, MCLIP_PATH_TCGEN05, "pair_lse");
   if (rc) return rc;
   if (!ref || !row_lse || !col_out || !status) { set_error("pair_lse: null ref/row_lse/col_out/status"); return MCLIP_ERR_INVALID; }
@@ -135,7 +135,7 @@ int mclip_pair_lse(const void* X, const void* Y, int64_t M, int64_t N, int64_t D
   }
   const size_t need = tc_pair_lse_ws(M, N, D);
   if (!ws || ws_bytes < need) { set_error("pair_lse: workspace %zu < %zu bytes", ws_bytes, need); return MCLIP_ERR_WORKSPACE; }
-  PairLseArgs a{X, Y, M, N, D, ldx, ldy, dtype, logit_scale, ref, row_lse, rowdot, col_out, col_mode, status, ws, ws_bytes,
+  PairLseArgs a{X, Y, M, N, D, ldx, ldy, dtype, logit_scale, ref, diag_off, diag, row_lse, rowdot, col_out, col_mode, status, ws, ws_bytes,
                 (cudaStream_t)cuda_stream};
   return tc_pair_lse(a);
 }

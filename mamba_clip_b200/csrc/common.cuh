@@ -63,6 +63,8 @@ struct PairLseArgs {
   int dtype;
   const float* logit_scale;
   const float* ref;
+  int64_t diag_off;
+  float* diag;       // may be null: [M], pre-filled by launch_pair_ref, overwritten with the accumulator's own dots
   float* row_lse;
   float* rowdot;     // may be null
   float* col_out;    // [N] column lse (col_mode 0) or [N + 2] raw column sums relative to ref, ref, status (col_mode 1)

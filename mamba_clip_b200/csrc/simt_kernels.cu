@@ -273,7 +273,8 @@ loss_finalize_kernel(const float* __restrict__ row_lse, const float* __restrict_
                      float* __restrict__ loss) {
   const float ls = ls_ptr[0];
   float acc = 0.f;
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x)
+#pragma unroll 8
+  for (int64_t i = threadIdx.x; i < n; i += 1024)     // unrolled: the loads of 8 iterations are in flight together
     acc += (row_lse[i] - ls * diag[i]) + (col_lse[i] - ls * diag[i]);
   const float tot = block_sum_1024(acc);
   if (threadIdx.x == 0) loss[0] = tot * (0.5f / (float)n);
@@ -284,7 +285,8 @@ dls_finalize_kernel(const float* __restrict__ u, const float* __restrict__ v, co
                     int64_t n, const float* __restrict__ go_ptr, float scale, float* __restrict__ t_out,
                     float* __restrict__ dls_out) {
   float acc = 0.f;
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) acc += (u[i] - diag[i]) + (v[i] - diag[i]);
+#pragma unroll 8
+  for (int64_t i = threadIdx.x; i < n; i += 1024) acc += (u[i] - diag[i]) + (v[i] - diag[i]);
   const float tot = block_sum_1024(acc);
   if (threadIdx.x == 0) {
     t_out[0] = tot;

@@ -1403,6 +1403,7 @@ prep_ly2_kernel(const float* __restrict__ lse_y, int64_t N, int64_t n_pad, float
   __shared__ float mu_s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float mn = INFINITY, mx = -INFINITY;
+#pragma unroll 8
   for (int64_t j = tid; j < N; j += 1024) {
     const float v = lse_y[j] * kLog2e - lw_col;
     mn = fminf(mn, v); mx = fmaxf(mx, v);
@@ -2179,7 +2180,11 @@ size_t tc_block_grad_ws(int64_t M, int64_t N, int64_t D) {
 int tc_row_lse(const RowLseArgs& a) {
   if (((uintptr_t)a.X | (uintptr_t)a.Y) & 15) { set_error("row_lse(tcgen05): X/Y must be 16-byte aligned"); return MCLIP_ERR_INVALID; }
   const bool pair = fwd_uses_pair(a.D);
-  const FwdPlan f = pair ? plan_fwd2(a.M, a.N, a.D) : plan_fwd(a.M, a.N, a.D);
+  FwdPlan f = pair ? plan_fwd2(a.M, a.N, a.D) : plan_fwd(a.M, a.N, a.D);
+  if (a.run_if) {   // chained fallback: normally exits at once, so keep the grid (= its launch cost) small
+    f.nsplit = 1;
+    f.tiles_per_split = f.tiles_total;
+  }
   if (f.stages < 2) { set_error("row_lse(tcgen05): not enough shared memory for D=%lld", (long long)a.D); return MCLIP_ERR_UNSUPPORTED; }
   CUtensorMap tmX, tmY;
   int rc = make_tmap(&tmX, a.X, a.M, a.D, a.ldx, a.dtype, 128);

@@ -53,6 +53,8 @@ struct PairParams {
   float* part_rs;       // [nsplit][M] row sums of e
   float* part_rc;       // [nsplit][M] row sums of e * <x_i, y_j>
   float* part_cs;       // [ceil(M / 128)][n_pad] column sums of e over each 128-row block
+  float* diag;          // [M] or null: overwritten with the accumulator's own <x_i, y_i+off> (see pair_chunk)
+  int64_t diag_off;
   int bf16;
 };
 
@@ -72,9 +74,13 @@ __device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t* v) 
 
 // One 32 x 32 block of S held as 4 rows (r + 8*ri) x 8 columns (8*(ci/2) + 2*qd + ci%2) per thread.
 // v[0..15]: lanes +0..15 of the quadrant, v[16..31]: lanes +16..31.
+// kMasked (tail tile in N, or a tile crossing the diagonal): columns >= N contribute nothing, and the positive-pair
+// dot is taken from the accumulator itself -- the loss subtracts ls * diag from an LSE that is dominated by the very
+// same product when the softmax is saturated, so both must carry the same tensor-core rounding.
 template <bool kMasked>
 __device__ __forceinline__ void pair_chunk(const uint32_t (&v)[32], float k2, const float (&bias)[4], int64_t colq,
-                                           int64_t N, float (&rs)[4], float (&rc)[4], float (&cs)[8]) {
+                                           int64_t N, float (&rs)[4], float (&rc)[4], float (&cs)[8],
+                                           const int64_t (&jd)[4], float* __restrict__ diag_rows) {
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     const int h = j >> 4, jj = j & 15, rep = jj >> 2;
@@ -82,7 +88,9 @@ __device__ __forceinline__ void pair_chunk(const uint32_t (&v)[32], float k2, co
     const float c = __uint_as_float(v[j]);
     float e = ex2_approx(fmaf(c, k2, bias[ri]));
     if (kMasked) {
-      if (colq + 8 * rep + (jj & 1) >= N) e = 0.f;
+      const int64_t col = colq + 8 * rep + (jj & 1);
+      if (col >= N) e = 0.f;
+      else if (col == jd[ri]) diag_rows[8 * ri] = c;
     }
     rs[ri] += e;
     rc[ri] = fmaf(e, c, rc[ri]);
@@ -217,13 +225,16 @@ tc_pair_lse2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     const float k2 = p.ls[0] * kLog2e;
     const float c0 = p.ref[0];
     float bias[4], rs[4], rc[4];
+    int64_t jd[4];
 #pragma unroll
     for (int ri = 0; ri < 4; ++ri) {
       const int64_t row = m0 + q * 32 + r + 8 * ri;
       bias[ri] = row < p.M ? -c0 : -INFINITY;   // rows past M hold TMA zero fill: e = 2^-inf = 0 in every sum
+      jd[ri] = (p.diag != nullptr && row < p.M) ? row + p.diag_off : -1;
       rs[ri] = 0.f;
       rc[ri] = 0.f;
     }
+    float* diag_rows = p.diag + (m0 + q * 32 + r);   // only dereferenced where jd matched (row < M)
     // column this lane owns after col_halving, inside a 32-column chunk
     const int own_col = 16 * ((lane >> 4) & 1) + 8 * ((lane >> 3) & 1) + 2 * qd + ((lane >> 2) & 1);
     float* part_cs_row = p.part_cs + (size_t)(m0 / 128) * p.n_pad;
@@ -234,7 +245,8 @@ tc_pair_lse2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       const int64_t n0 = (int64_t)(t0 + lt) * BN;
       mbar_wait(tfull_bar(buf), bph);
       tc_fence_after();
-      const bool tail = n0 + BN > p.N;
+      const bool tail = (n0 + BN > p.N) ||
+                        (p.diag != nullptr && n0 < m0 + p.diag_off + 128 && n0 + BN > m0 + p.diag_off);
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + half * kHalfCols;
       float* cb = colbuf + ((lt & 1) * 2 + half) * 512 + q * 128;
 #pragma unroll 1
@@ -253,8 +265,8 @@ tc_pair_lse2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         }
         float cs[8];
         const int64_t colq = n0 + half * kHalfCols + cc * 32 + 2 * qd;
-        if (tail) pair_chunk<true>(v, k2, bias, colq, p.N, rs, rc, cs);
-        else pair_chunk<false>(v, k2, bias, colq, p.N, rs, rc, cs);
+        if (tail) pair_chunk<true>(v, k2, bias, colq, p.N, rs, rc, cs, jd, diag_rows);
+        else pair_chunk<false>(v, k2, bias, colq, p.N, rs, rc, cs, jd, diag_rows);
         cb[cc * 32 + own_col] = col_halving(cs, lane);
       }
       // sum the four quadrants of this column half and write the 128-row-block partial
@@ -571,6 +583,7 @@ int tc_pair_lse(const PairLseArgs& a) {
   p.part_rs = reinterpret_cast<float*>(ws + w.rs);
   p.part_rc = reinterpret_cast<float*>(ws + w.rc);
   p.part_cs = reinterpret_cast<float*>(ws + w.cs);
+  p.diag = a.diag; p.diag_off = a.diag_off;
   p.bf16 = a.dtype == MCLIP_DTYPE_BF16;
   rc = tc_set_smem(reinterpret_cast<const void*>(tc_pair_lse2_kernel), f.smem);
   if (rc) return rc;

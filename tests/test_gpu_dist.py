@@ -115,9 +115,17 @@ def test_nccl_bf16_tensor_core_sizes_against_oracle(W):
     for j, job in enumerate(jobs):
         img, txt = _features(W, job)
         ref = O.ref_port_ranks(img.float(), txt.float(), job["ls"], W, job["local_loss"], job["gwg"], grad_output=2.0)
+        # saturated softmaxes (the ls = 100 job): true losses / gradients of ~1e-9 sit below the f32 rounding of an
+        # LSE of magnitude ls, so those comparisons carry the same absolute floors as the W = 1 tests
+        ls_, go_, Bl_ = job["ls"], job["go"], job["Bl"]
+        sat = ls_ >= 100.0
+        l_floor = 4 * 1.2e-7 * ls_ if sat else 1e-6
+        g_floor = 8 * 1.2e-7 * ls_ * go_ * ls_ / (2 * Bl_) * Bl_ ** 0.5 if sat else 0.0
+        d_floor = 1.2e-7 * go_ * ls_ * 20 if sat else 1e-7
         for r in range(W):
             loss, di, dt, dls = out[(j, r)]
-            assert abs(loss - float(ref[r].loss)) <= 2e-3 * abs(float(ref[r].loss)) + 1e-6
-            assert O.rel_err(torch.from_numpy(di), ref[r].d_image) <= 2e-3
-            assert O.rel_err(torch.from_numpy(dt), ref[r].d_text) <= 2e-3
-            assert abs(dls - float(ref[r].d_logit_scale)) <= 2e-3 * abs(float(ref[r].d_logit_scale)) + 1e-7
+            assert abs(loss - float(ref[r].loss)) <= 2e-3 * abs(float(ref[r].loss)) + l_floor
+            for got, want in ((di, ref[r].d_image), (dt, ref[r].d_text)):
+                err = float((torch.from_numpy(got).double() - want.double()).norm())
+                assert err <= 2e-3 * float(want.double().norm()) + g_floor
+            assert abs(dls - float(ref[r].d_logit_scale)) <= 2e-3 * abs(float(ref[r].d_logit_scale)) + d_floor

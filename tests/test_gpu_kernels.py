@@ -194,7 +194,7 @@ def test_pair_lse_two_sided_forward(dtype, M, N, D, ls, diag_off, corr):
     lsd = torch.tensor([ls], dtype=torch.float32, device="cuda")
     assert be.pair_supported(xd, yd)
     diag, ref, status = be.pair_ref(xd, yd, lsd, diag_off)
-    row_lse, rowdot, col_lse = be.pair_lse(xd, yd, lsd, ref, status, True)
+    row_lse, rowdot, col_lse = be.pair_lse(xd, yd, lsd, ref, status, True, diag=diag, diag_off=diag_off)
     torch.cuda.synchronize()
     assert int(status.item()) == 0
     ref_row, ref_diag = O.block_row_lse(x.float(), y.float(), ls, diag_off)
@@ -363,7 +363,9 @@ def test_symmetry_and_homogeneity_properties():
         outs.append((float(loss.detach()), a.grad.float(), b.grad.float(), float(s.grad), a.detach().float(), b.detach().float()))
     (l0, di0, dt0, ds0, a0, b0), (l1, di1, dt1, ds1, _, _) = outs
     assert abs(l0 - l1) <= 1e-6 * abs(l0) and abs(ds0 - ds1) <= 1e-5 * abs(ds0) + 1e-9
-    assert torch.equal(di0, dt1) and torch.equal(dt0, di1)
+    # the two-sided forward sums rows and columns in different orders, so the swapped run sees LSEs that differ in
+    # the last f32 bit: the bf16 gradients agree up to rare one-ulp flips rather than bit for bit
+    assert float((di0 - dt1).norm()) <= 5e-4 * float(dt1.norm()) and float((dt0 - di1).norm()) <= 5e-4 * float(di1.norm())
     e_i = float((a0 * di0).sum())
     e_t = float((b0 * dt0).sum())
     assert abs(e_i - 25.0 * ds0) <= 4e-3 * abs(25.0 * ds0) + 1e-6
