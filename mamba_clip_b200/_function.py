@@ -15,12 +15,13 @@ Per-rank values reproduce the reference exactly, including the W x factors (SURV
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import torch
 import torch.distributed as dist
 
-from . import _cabi
+from . import _cabi, _nccl
 
 _SUPPORTED = (torch.float32, torch.bfloat16, torch.float16)
 
@@ -54,6 +55,315 @@ def _compute_dtype(t: torch.Tensor) -> torch.dtype:
     return torch.float32
 
 
+class _EagerRunner:
+    """Runs every segment directly and allocates fresh buffers (the default path)."""
+
+    def seg(self, name, fn):
+        return fn()
+
+    def buffer(self, name, shape, dtype, device):
+        return torch.empty(shape, dtype=dtype, device=device)
+
+
+_EAGER = _EagerRunner()
+
+
+class _Done:
+    """Work handle of a collective that was issued in order on the compute stream: nothing to wait for."""
+
+    @staticmethod
+    def wait():
+        return None
+
+
+_side_streams = {}
+
+
+class _StreamJoin:
+    """Work handle of a collective issued on a side stream: `wait()` makes the current stream wait for it."""
+
+    def __init__(self, stream):
+        self.stream = stream
+
+    def wait(self):
+        torch.cuda.current_stream(self.stream.device).wait_stream(self.stream)
+
+
+def _gather_on_side_stream(out, x, comm):
+    """Direct NCCL all-gather on a per-device side stream (after everything already queued on the current stream);
+    the caller's stream keeps going and joins through the returned handle."""
+    dev = x.device
+    side = _side_streams.get(dev.index)
+    if side is None:
+        side = _side_streams[dev.index] = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        comm.all_gather(out, x)
+    return _StreamJoin(side)
+
+
+def _gather_into(out, x, group, comm=None):
+    """All-gather into a caller-provided buffer: directly through NCCL on the current stream when a direct
+    communicator exists (see _nccl.py), else through torch.distributed.  Returns a handle with `.wait()`."""
+    if comm is not None:
+        comm.all_gather(out, x)
+        return _Done
+    try:
+        return dist.all_gather_into_tensor(out, x, group=group, async_op=True)
+    except (RuntimeError, NotImplementedError):  # backends without the flat variant
+        return dist.all_gather(list(out.chunk(dist.get_world_size(group), dim=0)), x, group=group, async_op=True)
+
+
+def _forward_impl(be, xi, xt, ls, local_loss, gather_with_grad, rank, W, group, need_ls, run=_EAGER):
+    """Everything `ClipLoss.forward` launches, on already-cast contiguous inputs.  Returns the state dict that
+    `_backward_impl` consumes.  Kernel launches are grouped into segments (`run.seg`) separated by the collectives:
+    a segment is pure stream work without host synchronisation, so the graph runner can capture and replay it, while
+    the collectives always go through torch.distributed directly."""
+    Bl, D = xi.shape
+    dev = xi.device
+    comm = _nccl.direct_comm(group, dev) if (W > 1 and dev.type == "cuda") else None
+    comm_side = _nccl.direct_comm(group, dev, slot=1) if comm is not None else None
+    if W > 1:
+        # both gathers are in flight at once; the image gather (side stream / c10d's own stream) overlaps the first
+        # kernels, which only need the text features
+        all_t = run.buffer("all_t", (W * Bl, D), xt.dtype, dev)
+        all_i = run.buffer("all_i", (W * Bl, D), xi.dtype, dev)
+        work_t = _gather_into(all_t, xt, group, comm)
+        work_i = _gather_on_side_stream(all_i, xi, comm_side) if comm_side is not None else _gather_into(all_i, xi, group, comm)
+        off = int(rank) * Bl
+        work_t.wait()
+    else:
+        all_i, all_t, off = xi, xt, 0
+        work_i = None
+
+    # u, v: softmax-weighted raw dots (sum_j P_ij <x_i, y_j>) of the two blocks -- all d(logit_scale) needs
+    if getattr(be, "pair_supported", lambda *_: False)(xi, all_t):
+        # two-sided forward: one pass over the rank's row block S_r = ls * I_r T_all^T gives its row LSEs and the
+        # sums of every column over its rows (1 GEMM unit instead of 2).  At W > 1 the per-rank column sums are
+        # all-gathered (4 * (B_g + 2) bytes per rank) and each rank finishes its own columns.  The result is
+        # validated on the device; the predicated one-sided calls behind it redo the work with running maxima
+        # when the status flag was raised (they exit at once otherwise -- no host sync).
+        def seg_a():
+            diag, ref, status = be.pair_ref(xi, all_t, ls, off)
+            row_lse, u, col = be.pair_lse(xi, all_t, ls, ref, status, need_ls, col_mode=0 if W == 1 else 1, diag=diag,
+                                          diag_off=off)
+            return diag, status, row_lse, u, col
+        diag, status, row_lse, u, col = run.seg("fwd_a", seg_a)
+        if W > 1:
+            parts = run.buffer("col_parts", (W, col.numel()), torch.float32, dev)      # [W, B_g + 2]
+            _gather_into(parts, col.unsqueeze(0), group, comm).wait()
+            work_i.wait()
+
+        def seg_b():
+            col_lse = col if W == 1 else be.merge_col_sums(parts, W * Bl, off, Bl, status)
+            be.row_lse(xi, all_t, ls, off, False, need_ls, run_if=status, out_lse=row_lse, out_rowdot=u)
+            be.row_lse(xt, all_i, ls, off, False, False, run_if=status, out_lse=col_lse)
+            return col_lse, be.loss_finalize(row_lse, col_lse, diag, ls)      # the rank's local loss
+        col_lse, loss = run.seg("fwd_b", seg_b)
+        uv = (u, None) if need_ls else None   # v comes out of the text-side backward kernel
+    else:
+        if work_i is not None:
+            work_i.wait()
+
+        def seg_a():
+            r1 = be.row_lse(xi, all_t, ls, off, True, need_ls)       # rows R of S
+            r2 = be.row_lse(xt, all_i, ls, off, False, need_ls)      # columns R of S
+            return r1, r2, be.loss_finalize(r1[0], r2[0], r1[1], ls)
+        r1, r2, loss = run.seg("fwd_a", seg_a)
+        row_lse, diag, col_lse = r1[0], r1[1], r2[0]
+        uv = (r1[2], r2[2]) if need_ls else None
+    if W > 1 and not local_loss:
+        # reference: one global [B_g, B_g] problem on every rank == mean of the equal-sized rank losses
+        loss = loss.clone()
+        dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
+        loss = loss / W
+
+    own_terms_only = W > 1 and local_loss and not gather_with_grad
+    stats = stats_work = None
+    if W > 1 and not own_terms_only:
+        # the LSE vectors of the other ranks are only needed by backward: start the gather now, wait there
+        stats = run.buffer("stats", (W, 2, Bl), torch.float32, dev)
+        stats_work = _gather_into(stats, torch.stack((row_lse, col_lse)).unsqueeze(0), group, comm)
+    return dict(loss=loss, xi=xi, xt=xt, all_i=all_i, all_t=all_t, ls=ls, row_lse=row_lse, col_lse=col_lse, diag=diag,
+                uv=uv, stats=stats, stats_work=stats_work, off=off, own_terms_only=own_terms_only)
+
+
+def _backward_impl(be, st, go, local_loss, gather_with_grad, W, group, need_i, need_t, need_ls, run=_EAGER):
+    """Everything `ClipLoss` launches in backward.  -> (d_image, d_text, d_logit_scale as a 0-dim f32 tensor)."""
+    xi, xt, all_i, all_t, ls = st["xi"], st["xt"], st["all_i"], st["all_t"], st["ls"]
+    row_lse, col_lse, diag, off = st["row_lse"], st["col_lse"], st["diag"], st["off"]
+    own_terms_only = st["own_terms_only"]
+    if st["stats_work"] is not None:
+        st["stats_work"].wait()
+        st["stats_work"] = None
+    stats = st["stats"]
+    Bl = xi.shape[0]
+    Bg = W * Bl
+
+    # 1/(2n) of the feature gradients (SURVEY.md section 3.2): the true gradient for W=1 and (False, False),
+    # W x that otherwise.
+    n_feat = Bg if (W == 1 or (not local_loss and not gather_with_grad)) else Bl
+    inv_2n = 1.0 / (2.0 * n_feat)
+    need_ls = need_ls and st["uv"] is not None
+    # after a two-sided forward the text-side softmax-weighted dots v are still missing: the text-side
+    # backward kernel emits them as its `rowdot`
+    want_v = need_ls and st["uv"][1] is None
+    n_ls = Bl if (W > 1 and local_loss) else Bg
+
+    def seg():
+        if stats is not None:
+            row_lse_all = stats[:, 0, :].reshape(-1)
+            col_lse_all = stats[:, 1, :].reshape(-1)
+        else:
+            row_lse_all, col_lse_all = row_lse, col_lse
+        if own_terms_only:
+            w_row, w_col, w_diag = 1.0, 0.0, 1.0
+            lse_y_i = lse_y_t = None
+        else:
+            w_row, w_col, w_diag = 1.0, 1.0, 2.0
+            lse_y_i, lse_y_t = col_lse_all, row_lse_all
+        d_img = d_txt = t = d_ls = v_bwd = None
+        if need_i:
+            d_img, _ = be.block_grad(xi, all_t, ls, go, row_lse, lse_y_i, off, w_row, w_col, w_diag, inv_2n, False)
+        if need_t:
+            d_txt, v_bwd = be.block_grad(xt, all_i, ls, go, col_lse, lse_y_t, off, w_row, w_col, w_diag, inv_2n, want_v)
+        elif want_v:
+            v_bwd = be.row_lse(xt, all_i, ls, off, False, True)[2]
+        if need_ls:
+            u, v = st["uv"]
+            if v is None:
+                v = v_bwd
+            t, d_ls = be.dls_finalize(u, v, diag, go, 1.0 / (2.0 * n_ls))
+        return d_img, d_txt, t, d_ls
+    d_img, d_txt, t, d_ls = run.seg("bwd", seg)
+    if need_ls and W > 1 and not local_loss:
+        t = t.clone()
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        d_ls = go[0] * t / (2.0 * n_ls)
+    return d_img, d_txt, d_ls
+
+
+# ----------------------------------------------------------------------------------------------------
+# CUDA-graph replay of the launch segments (opt-in)
+# ----------------------------------------------------------------------------------------------------
+# One loss step is ~20 kernel launches and up to 4 collectives.  At the headline shapes on 8 GPUs the kernels of a rank
+# take ~0.5 ms, which is less than the Python / ctypes time needed to enqueue them: the step is host-bound.  With
+# graphs enabled, the kernel segments of a given (shape, dtype, mode) are captured once (after two eager warm-up calls)
+# and replayed; per call the host copies the inputs into the static buffers, issues the collectives (always eagerly,
+# between the segments, into static buffers: no NCCL kernel is ever captured) and replays.
+_GRAPHS_ENABLED = os.environ.get("MCLIP_CUDA_GRAPHS", "0") == "1"
+_GRAPH_WARMUP = 2
+_graph_cache = {}
+
+
+def enable_cuda_graphs(flag: bool = True) -> None:
+    """Replay captured CUDA graphs for the kernel segments of `ClipLoss` forward/backward (per shape/dtype/mode, after
+    two eager calls).  Same kernels, same results; removes the host launch overhead.  Also: MCLIP_CUDA_GRAPHS=1."""
+    global _GRAPHS_ENABLED
+    _GRAPHS_ENABLED = bool(flag)
+    if not flag:
+        _graph_cache.clear()
+
+
+def cuda_graphs_enabled() -> bool:
+    return _GRAPHS_ENABLED
+
+
+_SAVED_KEYS = ("xi", "xt", "all_i", "all_t", "ls", "row_lse", "col_lse", "diag")
+
+
+class _PendingToken:
+    """Lives on the autograd ctx of a graphed forward: if the ctx dies without a backward (loss discarded), the
+    graph's buffers are released for the next forward."""
+
+    def __init__(self, gl, generation):
+        self.gl, self.generation = gl, generation
+
+    def __del__(self):
+        gl = self.gl
+        if gl is not None and gl.pending and gl.generation == self.generation:
+            gl.pending = False
+
+
+class _GraphedLoss:
+    """Static buffers + the captured segment graphs for one (device, shape, dtype, mode) key."""
+
+    def __init__(self, xi, xt, cfg, need_ls):
+        self.cfg = cfg                       # (local_loss, gather_with_grad, rank, W, group)
+        self.need_ls = need_ls
+        self.calls = 0
+        self.xi = torch.empty_like(xi)
+        self.xt = torch.empty_like(xt)
+        self.ls = torch.empty(1, dtype=torch.float32, device=xi.device)
+        self.go = torch.ones(1, dtype=torch.float32, device=xi.device)
+        self.graphs = {}                     # segment name -> (CUDAGraph, outputs)
+        self.buffers = {}
+        self.state = None
+        self.pending = False                 # a forward is waiting for its backward: the statics must not be touched
+        self.generation = 0
+        self._prefix = ""
+        # One graph per direction (collectives included) when every collective of the step is a direct in-stream NCCL
+        # call; otherwise one graph per kernel segment with the collectives issued eagerly between them.
+        local_loss, _, _, W, group = cfg
+        self.whole = W == 1 or (os.environ.get("MCLIP_GRAPH_NCCL", "0") == "1" and local_loss and
+                                _nccl.direct_comm(group, xi.device) is not None)
+
+    # runner interface ---------------------------------------------------------------------------
+    def seg(self, name, fn):
+        key = self._prefix + name
+        hit = self.graphs.get(key)
+        if hit is None:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                outs = fn()
+            hit = self.graphs[key] = (g, outs)
+        hit[0].replay()
+        return hit[1]
+
+    def buffer(self, name, shape, dtype, device):
+        b = self.buffers.get(name)
+        if b is None:
+            b = self.buffers[name] = torch.empty(shape, dtype=dtype, device=device)
+        return b
+
+    # ---------------------------------------------------------------------------------------------
+    def run_forward(self, be, xi, xt, ls):
+        local_loss, gwg, rank, W, group = self.cfg
+        self.xi.copy_(xi)
+        self.xt.copy_(xt)
+        self.ls.copy_(ls)
+        self._prefix = ""
+        if self.whole:
+            if "fwd" not in self.graphs:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    st = _forward_impl(be, self.xi, self.xt, self.ls, local_loss, gwg, rank, W, group, self.need_ls)
+                self.graphs["fwd"] = (g, st)
+            g, self.state = self.graphs["fwd"]
+            g.replay()
+        else:
+            self.state = _forward_impl(be, self.xi, self.xt, self.ls, local_loss, gwg, rank, W, group, self.need_ls, run=self)
+        self.generation += 1
+        return self.state["loss"].clone()
+
+    def run_backward(self, be, go, need_i, need_t, need_ls):
+        local_loss, gwg, rank, W, group = self.cfg
+        self.go.copy_(go)
+        self._prefix = f"{int(need_i)}{int(need_t)}{int(need_ls)}:"
+        if self.whole:
+            key = self._prefix + "bwd_whole"
+            if key not in self.graphs:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    o = _backward_impl(be, self.state, self.go, local_loss, gwg, W, group, need_i, need_t, need_ls)
+                self.graphs[key] = (g, o)
+            g, outs = self.graphs[key]
+            g.replay()
+        else:
+            outs = _backward_impl(be, self.state, self.go, local_loss, gwg, W, group, need_i, need_t, need_ls, run=self)
+        return tuple(None if o is None else o.clone() for o in outs)
+
+
 class ClipLossFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, image_features, text_features, logit_scale, local_loss, gather_with_grad, rank, world_size,
@@ -68,61 +378,35 @@ class ClipLossFunction(torch.autograd.Function):
         else:
             ls = torch.full((1,), float(logit_scale), dtype=torch.float32, device=dev)
         W = int(world_size)
-        Bl = xi.shape[0]
-        if W > 1:
-            # both gathers are in flight at once; the image gather overlaps the first kernel
-            all_t, work_t = _gather_rows_async(xt, W, group)
-            all_i, work_i = _gather_rows_async(xi, W, group)
-            off = int(rank) * Bl
-            work_t.wait()
-        else:
-            all_i, all_t, off = xi, xt, 0
-            work_i = None
-
-        # u, v: softmax-weighted raw dots (sum_j P_ij <x_i, y_j>) of the two blocks -- all d(logit_scale) needs
         need_ls = torch.is_tensor(logit_scale) and logit_scale.requires_grad
-        if getattr(be, "pair_supported", lambda *_: False)(xi, all_t):
-            # two-sided forward: one pass over the rank's row block S_r = ls * I_r T_all^T gives its row LSEs and the
-            # sums of every column over its rows (1 GEMM unit instead of 2).  At W > 1 the per-rank column sums are
-            # all-gathered (4 * (B_g + 2) bytes per rank) and each rank finishes its own columns.  The result is
-            # validated on the device; the predicated one-sided calls behind it redo the work with running maxima
-            # when the status flag was raised (they exit at once otherwise -- no host sync).
-            diag, ref, status = be.pair_ref(xi, all_t, ls, off)
-            if W == 1:
-                row_lse, u, col_lse = be.pair_lse(xi, all_t, ls, ref, status, need_ls, diag=diag, diag_off=off)
-            else:
-                row_lse, u, col_part = be.pair_lse(xi, all_t, ls, ref, status, need_ls, col_mode=1, diag=diag, diag_off=off)
-                parts = _gather_rows(col_part.unsqueeze(0), W, group)           # [W, B_g + 2]
-                col_lse = be.merge_col_sums(parts, W * Bl, off, Bl, status)
-                work_i.wait()
-            be.row_lse(xi, all_t, ls, off, False, need_ls, run_if=status, out_lse=row_lse, out_rowdot=u)
-            be.row_lse(xt, all_i, ls, off, False, False, run_if=status, out_lse=col_lse)
-            ctx.uv = (u, None) if need_ls else None   # v comes out of the text-side backward kernel
-        else:
-            r1 = be.row_lse(xi, all_t, ls, off, True, need_ls)       # rows R of S
-            if work_i is not None:
-                work_i.wait()
-            r2 = be.row_lse(xt, all_i, ls, off, False, need_ls)      # columns R of S
-            row_lse, diag, col_lse = r1[0], r1[1], r2[0]
-            ctx.uv = (r1[2], r2[2]) if need_ls else None
-        loss = be.loss_finalize(row_lse, col_lse, diag, ls)      # the rank's local loss
-        if W > 1 and not local_loss:
-            # reference: one global [B_g, B_g] problem on every rank == mean of the equal-sized rank losses
-            dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
-            loss = loss / W
+        wants_grad = need_ls or image_features.requires_grad or text_features.requires_grad
 
-        own_terms_only = W > 1 and local_loss and not gather_with_grad
-        ctx.stats_work = None
-        if W > 1 and not own_terms_only:
-            # the LSE vectors of the other ranks are only needed by backward: start the gather now, wait there
-            stats, ctx.stats_work = _gather_rows_async(torch.stack((row_lse, col_lse)).unsqueeze(0), W, group)  # [W, 2, B_l]
-        else:
-            stats = None   # W == 1, or own-row terms only: the local vectors are all backward needs
+        ctx.graphed = None
+        if _GRAPHS_ENABLED and dev.type == "cuda" and _cabi._override is None and not torch.cuda.is_current_stream_capturing():
+            key = (dev.index, tuple(xi.shape), cdt, bool(local_loss), bool(gather_with_grad), int(rank), W, id(group), need_ls)
+            gl = _graph_cache.get(key)
+            if gl is None:
+                gl = _graph_cache[key] = _GraphedLoss(xi, xt, (bool(local_loss), bool(gather_with_grad), int(rank), W, group), need_ls)
+            gl.calls += 1
+            if gl.calls > _GRAPH_WARMUP and not gl.pending:
+                loss = gl.run_forward(be, xi, xt, ls)
+                if wants_grad:
+                    gl.pending = True
+                    ctx.graphed = gl
+                    ctx.generation = gl.generation
+                    ctx.token = _PendingToken(gl, gl.generation)
+                ctx.cfg = (bool(local_loss), bool(gather_with_grad), W, group)
+                ctx.in_dtypes = (image_features.dtype, text_features.dtype)
+                ctx.ls_meta = (logit_scale.dtype, logit_scale.shape, logit_scale.device) if torch.is_tensor(logit_scale) else None
+                return loss
 
-        # `stats` is written by the in-flight collective, so it is kept off autograd's version tracking
-        ctx.stats = stats
-        ctx.save_for_backward(xi, xt, all_i, all_t, ls, row_lse, col_lse, diag)
-        ctx.cfg = (bool(local_loss), bool(gather_with_grad), W, off, own_terms_only, group)
+        st = _forward_impl(be, xi, xt, ls, bool(local_loss), bool(gather_with_grad), int(rank), W, group, need_ls)
+        loss = st.pop("loss")
+        # tensors go through save_for_backward (in-place modification checks); `stats` is written by an in-flight
+        # collective, so it is kept off autograd's version tracking together with the non-tensor state
+        ctx.save_for_backward(*(st.pop(k) for k in _SAVED_KEYS))
+        ctx.state = st
+        ctx.cfg = (bool(local_loss), bool(gather_with_grad), W, group)
         ctx.in_dtypes = (image_features.dtype, text_features.dtype)
         ctx.ls_meta = (logit_scale.dtype, logit_scale.shape, logit_scale.device) if torch.is_tensor(logit_scale) else None
         return loss
@@ -130,62 +414,29 @@ class ClipLossFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         be = _cabi.get_backend()
-        xi, xt, all_i, all_t, ls, row_lse, col_lse, diag = ctx.saved_tensors
-        stats = ctx.stats
-        local_loss, gather_with_grad, W, off, own_terms_only, group = ctx.cfg
-        if ctx.stats_work is not None:
-            ctx.stats_work.wait()
-            ctx.stats_work = None
-        if stats is not None:
-            row_lse_all = stats[:, 0, :].reshape(-1)
-            col_lse_all = stats[:, 1, :].reshape(-1)
-        else:
-            row_lse_all, col_lse_all = row_lse, col_lse
-        Bl = xi.shape[0]
-        Bg = W * Bl
-        go = grad_out.detach().to(device=xi.device, dtype=torch.float32).reshape(1).contiguous()
-
-        # 1/(2n) of the feature gradients: the true gradient for W=1 and (False, False),
-        # W x that otherwise.
-        n_feat = Bg if (W == 1 or (not local_loss and not gather_with_grad)) else Bl
-        inv_2n = 1.0 / (2.0 * n_feat)
-        if own_terms_only:
-            w_row, w_col, w_diag = 1.0, 0.0, 1.0
-            lse_y_i = lse_y_t = None
-        else:
-            w_row, w_col, w_diag = 1.0, 1.0, 2.0
-            lse_y_i, lse_y_t = col_lse_all, row_lse_all
-
+        local_loss, gather_with_grad, W, group = ctx.cfg
         need_i, need_t, need_ls = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
-        need_ls = need_ls and ctx.ls_meta is not None and ctx.uv is not None
-        # after a two-sided forward the text-side softmax-weighted dots v are still missing: the text-side
-        # backward kernel emits them as its `rowdot`
-        want_v = need_ls and ctx.uv[1] is None
-        d_img = d_txt = d_ls = v_bwd = None
-        if need_i:
-            d_img, _ = be.block_grad(xi, all_t, ls, go, row_lse, lse_y_i, off, w_row, w_col, w_diag, inv_2n, False)
-        if need_t:
-            d_txt, v_bwd = be.block_grad(xt, all_i, ls, go, col_lse, lse_y_t, off, w_row, w_col, w_diag, inv_2n, want_v)
-        elif want_v:
-            v_bwd = be.row_lse(xt, all_i, ls, off, False, True)[2]
-        if need_ls:
-            u, v = ctx.uv
-            if v is None:
-                v = v_bwd
-            n_ls = Bl if (W > 1 and local_loss) else Bg
-            t, d_ls = be.dls_finalize(u, v, diag, go, 1.0 / (2.0 * n_ls))
-            if W > 1 and not local_loss:
-                t = t.clone()
-                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-                d_ls = go[0] * t / (2.0 * n_ls)
+        need_ls = need_ls and ctx.ls_meta is not None
+        gl = ctx.graphed
+        if gl is not None:
+            if ctx.generation != gl.generation:
+                raise RuntimeError("mamba_clip_b200: the CUDA-graph buffers of this loss were overwritten by a later forward; "
+                                   "call backward before the next forward of the same shape, or disable CUDA graphs")
+            go = grad_out.detach().to(device=gl.go.device, dtype=torch.float32).reshape(1)
+            d_img, d_txt, d_ls = gl.run_backward(be, go, need_i, need_t, need_ls)
+            gl.pending = False   # (a second backward through retain_graph stays valid until the next forward)
+        else:
+            st = dict(ctx.state)
+            st.update(zip(_SAVED_KEYS, ctx.saved_tensors))
+            go = grad_out.detach().to(device=st["xi"].device, dtype=torch.float32).reshape(1).contiguous()
+            d_img, d_txt, d_ls = _backward_impl(be, st, go, local_loss, gather_with_grad, W, group, need_i, need_t, need_ls)
+        if d_ls is not None:
             dt, shape, dev = ctx.ls_meta
             d_ls = d_ls.reshape(shape).to(device=dev, dtype=dt)
-        else:
-            d_ls = None
         if d_img is not None:
-            d_img = d_img.to(ctx.in_dtypes[0]) if need_i else None
+            d_img = d_img.to(ctx.in_dtypes[0])
         if d_txt is not None:
-            d_txt = d_txt.to(ctx.in_dtypes[1]) if need_t else None
+            d_txt = d_txt.to(ctx.in_dtypes[1])
         return d_img, d_txt, d_ls, None, None, None, None, None
 
 

@@ -41,14 +41,23 @@ def _features(W, job):
 
 
 def _worker(rank, W, port, jobs, q):
+    import threading
+    wd = threading.Timer(420.0, lambda: os._exit(3))        # a hung collective must not outlive the test
+    wd.daemon = True
+    wd.start()
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=W, device_id=dev)
     try:
+        import mamba_clip_b200
         from mamba_clip_b200 import ClipLoss
         for j, job in enumerate(jobs):
+            # "graphs": the step is repeated so that the last repetition replays the captured CUDA graphs (collectives
+            # included); every repetition must give the same result
+            mamba_clip_b200.enable_cuda_graphs(bool(job.get("graphs")))
+            reps = 5 if job.get("graphs") else 1
             Bl, D = job["Bl"], job["D"]
             dtype = getattr(torch, job["dtype"])
             img, txt = _features(W, job)
@@ -56,9 +65,12 @@ def _worker(rank, W, port, jobs, q):
             b = txt[rank * Bl:(rank + 1) * Bl].to(dev).requires_grad_(True)
             ls = torch.tensor(job["ls"], device=dev, requires_grad=True)
             crit = ClipLoss(job["local_loss"], job["gwg"], True, rank, W)
-            loss = crit(a, b, ls)["contrastive_loss"]
-            loss.backward(torch.tensor(job["go"], device=dev))
+            for _ in range(reps):
+                a.grad = b.grad = ls.grad = None
+                loss = crit(a, b, ls)["contrastive_loss"]
+                loss.backward(torch.tensor(job["go"], device=dev))
             q.put((j, rank, float(loss.detach()), a.grad.float().cpu().numpy(), b.grad.float().cpu().numpy(), float(ls.grad)))
+        mamba_clip_b200.enable_cuda_graphs(False)
         dist.barrier()
     finally:
         dist.destroy_process_group()
@@ -111,6 +123,9 @@ def test_nccl_bf16_tensor_core_sizes_against_oracle(W):
                              local_loss=local_loss, gwg=gwg))
     jobs.append(dict(Bl=256, D=512, dtype="bfloat16", seed=78, corr=True, ls=100.0, go=2.0, local_loss=True, gwg=True,
                      adv=True))
+    for local_loss, gwg in ((True, True), (False, False)):
+        jobs.append(dict(Bl=256, D=512, dtype="bfloat16", seed=79, corr=True, ls=20.0, go=2.0, local_loss=local_loss, gwg=gwg,
+                         graphs=True))
     out = _run(W, jobs)
     for j, job in enumerate(jobs):
         img, txt = _features(W, job)
