@@ -158,6 +158,14 @@ int mclip_normalize_rows(const float* x, int64_t M, int64_t D, int64_t ldx, floa
 int mclip_normalize_rows_bwd(const float* x, const void* g, int64_t M, int64_t D, int64_t ldx, int64_t ldg, int g_dtype,
                              float eps, float* dx, int64_t lddx, void* cuda_stream);
 
+/*
+ * Measurement hook (bench.py's roofline leg; never used by the loss itself).  enable = 1: from now on every launch of
+ * the dominant kernel (the CTA-pair backward kernel behind mclip_block_grad) is bracketed by two CUDA events on its own
+ * stream.  enable = 0 / 2: stop (0) or keep going (2), synchronise the recorded events and return their summed duration
+ * in *total_ms and their number in *count (either may be NULL); the record list is cleared.
+ */
+int mclip_kernel_timing(int enable, float* total_ms, int* count);
+
 /* Number of kernel launches issued by this library on the calling thread since load (bench.py's
  * "gpu_launches" counter). */
 int64_t mclip_launch_count(void);

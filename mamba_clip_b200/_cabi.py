@@ -48,6 +48,7 @@ _SIGNATURES = {
     "mclip_loss_finalize": (ctypes.c_int, [_c_f32p, _c_f32p, _c_f32p, ctypes.c_int64, _c_f32p, _c_f32p, ctypes.c_void_p]),
     "mclip_dls_finalize": (ctypes.c_int, [_c_f32p, _c_f32p, _c_f32p, ctypes.c_int64, _c_f32p, ctypes.c_float, _c_f32p,
                                           _c_f32p, ctypes.c_void_p]),
+    "mclip_kernel_timing": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)]),
     "mclip_normalize_rows": (ctypes.c_int, [_c_f32p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_float, ctypes.c_int,
                                             ctypes.c_void_p, ctypes.c_int64, _c_f32p, ctypes.c_void_p]),
     "mclip_normalize_rows_bwd": (ctypes.c_int, [_c_f32p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
@@ -138,6 +139,16 @@ class CudaBackend:
         if buf is None or buf.numel() < need:
             buf = self._ws_buf[bkey] = torch.empty(need, dtype=torch.uint8, device=dev)
         return buf, need
+
+    def kernel_timing(self, enable: bool):
+        """enable=True: start bracketing every launch of the dominant (pair backward) kernel with CUDA events.
+        enable=False: stop and return (total_ms, launches) of what was recorded."""
+        if enable:
+            _check(self.lib, self.lib.mclip_kernel_timing(1, None, None), "mclip_kernel_timing")
+            return None
+        tot, n = ctypes.c_float(0.0), ctypes.c_int(0)
+        _check(self.lib, self.lib.mclip_kernel_timing(0, ctypes.byref(tot), ctypes.byref(n)), "mclip_kernel_timing")
+        return tot.value, n.value
 
     def launch_count(self) -> int:
         return int(self.lib.mclip_launch_count())

@@ -253,6 +253,10 @@ def _backward_impl(be, st, go, local_loss, gather_with_grad, W, group, need_i, n
 # between the segments, into static buffers: no NCCL kernel is ever captured) and replays.
 _GRAPHS_ENABLED = os.environ.get("MCLIP_CUDA_GRAPHS", "0") == "1"
 _GRAPH_WARMUP = 2
+# Replay only pays where the step is launch-bound.  From ~2^37 multiply-adds per rank and pass (B_l * B_g * D; the
+# headline C3 shape is 2^36 at 8 GPUs, 2^37 at 4 and 2^39 at one) the kernels outlast the host by a wide margin, and
+# the static input copies / output clones of the graph path (4 x B_l x D elements) would only add traffic.
+_GRAPH_MAX_WORK = int(os.environ.get("MCLIP_GRAPH_MAX_WORK", str(1 << 37)))
 _graph_cache = {}
 
 
@@ -382,7 +386,9 @@ class ClipLossFunction(torch.autograd.Function):
         wants_grad = need_ls or image_features.requires_grad or text_features.requires_grad
 
         ctx.graphed = None
-        if _GRAPHS_ENABLED and dev.type == "cuda" and _cabi._override is None and not torch.cuda.is_current_stream_capturing():
+        if (_GRAPHS_ENABLED and dev.type == "cuda" and _cabi._override is None
+                and xi.shape[0] * xi.shape[0] * W * xi.shape[1] < _GRAPH_MAX_WORK
+                and not torch.cuda.is_current_stream_capturing()):
             key = (dev.index, tuple(xi.shape), cdt, bool(local_loss), bool(gather_with_grad), int(rank), W, id(group), need_ls)
             gl = _graph_cache.get(key)
             if gl is None:

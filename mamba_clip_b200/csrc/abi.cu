@@ -186,6 +186,12 @@ int mclip_dls_finalize(const float* u, const float* v, const float* diag, int64_
   return launch_dls_finalize(u, v, diag, n, grad_out, scale, t_out, dls_out, (cudaStream_t)cuda_stream);
 }
 
+int mclip_kernel_timing(int enable, float* total_ms, int* count) {
+  if (enable == 1) { kernel_timing_enable(true); return MCLIP_OK; }
+  if (enable == 0) kernel_timing_enable(false);
+  return kernel_timing_read(total_ms, count);
+}
+
 int mclip_normalize_rows(const float* x, int64_t M, int64_t D, int64_t ldx, float eps, int out_dtype, void* y, int64_t ldy,
                          float* inv_norm, void* cuda_stream) {
   if (!x || !y || M <= 0 || D <= 0 || ldx < D || ldy < D || !valid_dtype(out_dtype) || !(eps > 0.f)) { set_error("normalize_rows: invalid argument"); return MCLIP_ERR_INVALID; }

@@ -113,6 +113,10 @@ int launch_lse_from_sum(const float* sum, int64_t n, const float* ref, float* ls
 int launch_merge_col_sums(const float* parts, int W, int64_t stride, int64_t n_total, int64_t col0, int64_t n, float* lse,
                           int* status, cudaStream_t stream);
 
+// in-situ timing of the dominant kernel (tc_kernels.cu); used by bench.py's roofline leg only
+void kernel_timing_enable(bool on);
+int kernel_timing_read(float* total_ms, int* count);
+
 // shared small kernels -- simt_kernels.cu
 // merge `nsplit` partial (max2, sum, sum*c) triples per row into a natural-log LSE (+ rowdot if asked for).
 int launch_lse_merge(const float* part_m2, const float* part_s, const float* part_c, int nsplit, int64_t M, float* lse,

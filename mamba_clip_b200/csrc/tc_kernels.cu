@@ -14,6 +14,8 @@
 #include <cstdlib>
 #include <mutex>
 #include <unordered_map>
+#include <utility>
+#include <vector>
 
 #include "common.cuh"
 #include "sm100_ptx.cuh"
@@ -2718,6 +2720,62 @@ int set_smem(K kernel, uint32_t bytes) {
 
 }  // namespace
 
+// ---- optional in-situ timing of the dominant kernel (bench.py's roofline leg) --------------------------------
+// While enabled, every launch of the pair backward kernel is bracketed by two CUDA events on its own stream; reading
+// synchronises those events and returns the summed duration.  Off by default: the product path records nothing.
+namespace {
+std::mutex g_timing_mu;
+bool g_timing_on = false;
+std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_timing_events;
+}  // namespace
+
+void kernel_timing_enable(bool on) {
+  std::lock_guard<std::mutex> lock(g_timing_mu);
+  g_timing_on = on;
+}
+
+int kernel_timing_read(float* total_ms, int* count) {
+  std::lock_guard<std::mutex> lock(g_timing_mu);
+  float tot = 0.f;
+  int n = 0;
+  for (auto& ev : g_timing_events) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(ev.second) == cudaSuccess && cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) {
+      tot += ms;
+      ++n;
+    }
+    cudaEventDestroy(ev.first);
+    cudaEventDestroy(ev.second);
+  }
+  g_timing_events.clear();
+  (void)cudaGetLastError();
+  if (total_ms) *total_ms = tot;
+  if (count) *count = n;
+  return MCLIP_OK;
+}
+
+namespace {
+struct ScopedKernelTimer {
+  cudaEvent_t a = nullptr, b = nullptr;
+  cudaStream_t stream;
+  bool active = false;
+  explicit ScopedKernelTimer(cudaStream_t s) : stream(s) {
+    std::lock_guard<std::mutex> lock(g_timing_mu);
+    if (!g_timing_on) return;
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) return;
+    if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+    active = cudaEventRecord(a, s) == cudaSuccess;
+  }
+  ~ScopedKernelTimer() {
+    if (!active) return;
+    cudaEventRecord(b, stream);
+    std::lock_guard<std::mutex> lock(g_timing_mu);
+    g_timing_events.emplace_back(a, b);
+  }
+};
+}  // namespace
+
 int tc_make_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t D, int64_t ld, int dtype, uint32_t box_rows) {
   return make_tmap(map, base, rows, D, ld, dtype, box_rows);
 }
@@ -3089,12 +3147,15 @@ int tc_block_grad2(const BlockGradArgs& a) {
     MCLIP_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_block_grad2_kernel<BF, PAIRS, GT>, tmX, tmY, tmY16, p)); \
   } while (0)
   const bool gt = g_in_tmem();
-  if (b.cpairs == 2) {            // multicast variant: shared-memory G only
-    if (bf) MCLIP_LAUNCH_BWD2(true, 2, false); else MCLIP_LAUNCH_BWD2(false, 2, false);
-  } else if (gt) {
-    if (bf) MCLIP_LAUNCH_BWD2(true, 1, true); else MCLIP_LAUNCH_BWD2(false, 1, true);
-  } else {
-    if (bf) MCLIP_LAUNCH_BWD2(true, 1, false); else MCLIP_LAUNCH_BWD2(false, 1, false);
+  {
+    ScopedKernelTimer timer(a.stream);   // no-op unless bench.py asked for in-situ timing; brackets only this launch
+    if (b.cpairs == 2) {            // multicast variant: shared-memory G only
+      if (bf) MCLIP_LAUNCH_BWD2(true, 2, false); else MCLIP_LAUNCH_BWD2(false, 2, false);
+    } else if (gt) {
+      if (bf) MCLIP_LAUNCH_BWD2(true, 1, true); else MCLIP_LAUNCH_BWD2(false, 1, true);
+    } else {
+      if (bf) MCLIP_LAUNCH_BWD2(true, 1, false); else MCLIP_LAUNCH_BWD2(false, 1, false);
+    }
   }
 #undef MCLIP_LAUNCH_BWD2
   count_launch();

@@ -62,7 +62,8 @@ def test_producer_into_loss_chain_matches_fp64_chain():
     lab = torch.arange(B)
     ref = (F.cross_entropy(logits, lab) + F.cross_entropy(logits.T, lab)) / 2
     ref.backward()
-    assert abs(float(loss.detach()) - float(ref)) <= 2e-3 * abs(float(ref))
+    # the loss is ~4e-6 here (saturated softmax): one f32 ulp of an LSE of magnitude ls is the absolute floor
+    assert abs(float(loss.detach()) - float(ref)) <= 2e-3 * abs(float(ref)) + 1.2e-7 * ls
     # dLoss/dfeature arrives in bf16 (1.6e-3 of its norm); the normalisation backward then removes its radial
     # component, so the rounding error is relative to the *full* feature gradient while the result is only its
     # tangential part: allow the amplification |g| / |g_tangential| (the reference's AMP path rounds the same way)
