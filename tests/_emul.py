@@ -11,7 +11,10 @@ class EmulatedBackend:
     def __init__(self):
         self.calls = []
 
-    def row_lse(self, X, Y, ls, diag_off, want_diag, want_rowdot=False):
+    def row_lse(self, X, Y, ls, diag_off, want_diag, want_rowdot=False, run_if=None, out_lse=None, out_rowdot=None):
+        if run_if is not None and int(run_if) == 0:
+            self.calls.append("row_lse(skipped)")      # predicated off: nothing is written
+            return (out_lse, None, out_rowdot) if want_rowdot else (out_lse, None)
         self.calls.append("row_lse")
         lse, diag = O.block_row_lse(X, Y, float(ls), diag_off)
         out = (lse.float(), (diag.float() if want_diag else None))
@@ -19,6 +22,10 @@ class EmulatedBackend:
             C = X.double() @ Y.double().T
             P = torch.exp(float(ls) * C - lse[:, None])
             out = out + ((P * C).sum(dim=1).float(),)
+        if run_if is not None:                          # predicated on: results land in the caller's buffers
+            out_lse.copy_(out[0])
+            if want_rowdot:
+                out_rowdot.copy_(out[2])
         return out
 
     def block_grad(self, X, Y, ls, go, lse_x, lse_y, diag_off, w_row, w_col, w_diag, inv_2n, want_rowdot=True):
@@ -39,3 +46,74 @@ class EmulatedBackend:
 
     def launch_count(self):
         return len(self.calls)
+
+
+LOG2E = 1.4426950408889634
+LN2 = 0.6931471805599453
+SUM_LO, SUM_HI = 2.0 ** -75, 2.0 ** 120
+
+
+class EmulatedPairBackend(EmulatedBackend):
+    """Adds the oracle statement of the two-sided forward primitives (include/mclip_b200.h: mclip_pair_ref,
+    mclip_pair_lse, mclip_merge_col_sums, mclip_lse_from_sum), so that the host logic around them -- the column-sum
+    exchange, the status flag and the predicated fallback -- runs on CPU under gloo.  Arithmetic mirrors the kernels:
+    f32 exponent range (values below 2^-126 flush to zero, above 2^128 overflow), sums in f64."""
+
+    name = "oracle-emulation (two-sided forward)"
+
+    def pair_supported(self, X, Y):
+        return True
+
+    def pair_ref(self, X, Y, ls, diag_off):
+        self.calls.append("pair_ref")
+        M, N = X.shape[0], Y.shape[0]
+        idx = torch.arange(M) + diag_off
+        ok = (idx >= 0) & (idx < N)
+        diag = torch.zeros(M, dtype=torch.float64)
+        diag[ok] = (X.double()[ok] * Y.double()[idx[ok]]).sum(dim=1)
+        k2 = float(ls) * LOG2E
+        c0 = float(torch.maximum(k2 * diag[ok].max(), k2 * diag[ok].min())) - 40.0 if bool(ok.any()) else 0.0
+        return diag.float(), torch.tensor([c0], dtype=torch.float32), torch.zeros(1, dtype=torch.int32)
+
+    def pair_lse(self, X, Y, ls, ref, status, want_rowdot, col_mode=0, diag=None, diag_off=0):
+        self.calls.append("pair_lse")
+        C = X.double() @ Y.double().T
+        c0 = float(ref)
+        t = (float(ls) * LOG2E * C - c0).clamp(max=127.99)
+        e = torch.where(t < -126.0, torch.zeros_like(t), torch.exp2(t))          # f32 range of ex2.approx.ftz
+        e = torch.where(t >= 127.99, torch.full_like(t, float("inf")), e)
+        rs, cs = e.sum(dim=1), e.sum(dim=0)
+        if not bool(((rs >= SUM_LO) & (rs <= SUM_HI)).all()):
+            status |= 1
+        row_lse = ((c0 + torch.log2(rs)) * LN2).float()
+        rowdot = ((e * C).sum(dim=1) / rs).float() if want_rowdot else None
+        if col_mode == 0:
+            if not bool(((cs >= SUM_LO) & (cs <= SUM_HI)).all()):
+                status |= 2
+            return row_lse, rowdot, ((c0 + torch.log2(cs)) * LN2).float()
+        if not bool((cs <= SUM_HI).all()):
+            status |= 2
+        out = torch.empty(Y.shape[0] + 2, dtype=torch.float32)
+        out[:-2] = cs.float()
+        out[-2] = c0
+        out[-1:] = status.view(torch.float32)
+        return row_lse, rowdot, out
+
+    def merge_col_sums(self, parts, n_total, col0, n, status):
+        self.calls.append("merge_col_sums")
+        refs = parts[:, n_total].double()
+        bits = parts[:, n_total + 1].contiguous().view(torch.int32)
+        for b in bits.tolist():
+            status |= b
+        m = refs.max()
+        tot = (parts[:, col0:col0 + n].double() * torch.exp2(refs - m)[:, None]).sum(dim=0)
+        if not bool(((tot >= SUM_LO) & (tot <= SUM_HI)).all()):
+            status |= 2
+        return ((m + torch.log2(tot)) * LN2).float()
+
+    def lse_from_sum(self, sums, ref, status):
+        self.calls.append("lse_from_sum")
+        s = sums.double()
+        if not bool(((s >= SUM_LO) & (s <= SUM_HI)).all()):
+            status |= 2
+        return ((float(ref) + torch.log2(s)) * LN2).float()

@@ -54,6 +54,19 @@ def test_argument_validation_without_gpu(lib):
     assert rc == 1
     assert lib.mclip_loss_finalize(None, None, None, 4, None, None, None) == 1
     assert lib.mclip_dls_finalize(None, None, None, 4, None, 1.0, None, None, None) == 1
+    # two-sided forward entry points
+    assert lib.mclip_pair_ref(None, None, 4, 4, 8, 8, 8, 1, None, 0, None, None, None, None, 0, None) == 1
+    assert lib.mclip_pair_lse(None, None, 4, 4, 8, 8, 8, 1, None, None, 0, None, None, None, None, 0, None, None, 0, None) == 1
+    assert lib.mclip_merge_col_sums(None, 2, 10, 8, 0, 4, None, None, None) == 1
+    assert lib.mclip_lse_from_sum(None, 4, None, None, None, None) == 1
+    assert lib.mclip_pair_supported(4096, 4096, 512, 512, 512, 1) == 1        # bf16, D <= 512
+    assert lib.mclip_pair_supported(4096, 4096, 768, 768, 768, 1) == 0        # D > 512: one-sided kernels
+    assert lib.mclip_pair_supported(4096, 4096, 512, 512, 512, 0) == 0        # fp32: FFMA path
+    for op in (2, 3):                                                          # PAIR_LSE, PAIR_REF workspaces
+        assert lib.mclip_workspace_bytes(32768, 32768, 512, 1, op, 0, ctypes.byref(n)) == 0 and n.value > 0
+    # the measurement hook can be read without a GPU (nothing recorded)
+    tot, cnt = ctypes.c_float(-1.0), ctypes.c_int(-1)
+    assert lib.mclip_kernel_timing(0, ctypes.byref(tot), ctypes.byref(cnt)) == 0 and cnt.value == 0 and tot.value == 0.0
 
 
 def test_path_selection(lib):

@@ -34,8 +34,10 @@ def _features(W, job):
     dtype = getattr(torch, job["dtype"])
     img, txt = O.make_features(W * job["Bl"], job["D"], seed=job["seed"], correlated=job["corr"])
     if job.get("adv"):
-        # the first half of the global batch has every logit ~ls nats below the other half's positives: the two-sided
-        # forward of the ranks owning those rows leaves its f32 window, which must switch ALL ranks to the robust path
+        # identical pairs (cos = 1), then the first half of the image rows shrunk: at ls = 100 every logit of the first
+        # half's columns lies ~80 log2 units below the other half's positives, so the two-sided forward of the ranks
+        # owning those columns leaves its f32 window and they must take the predicated one-sided path
+        txt = img.clone()
         img[: W * job["Bl"] // 2] *= 0.01
     return img.to(dtype), txt.to(dtype)
 

@@ -148,20 +148,80 @@ def _worker(rank, case, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=case["W"])
     try:
         from mamba_clip_b200 import ClipLoss, _cabi
-        from tests._emul import EmulatedBackend
-        _cabi.set_backend_override(EmulatedBackend())
+        from tests._emul import EmulatedBackend, EmulatedPairBackend
+        be = EmulatedPairBackend() if case.get("pair") else EmulatedBackend()
+        _cabi.set_backend_override(be)
         W, Bl = case["W"], case["Bl"]
         img, txt = O.make_features(W * Bl, case["D"], seed=case["seed"], correlated=case["corr"])
+        if case.get("adv"):
+            # identical pairs (cos = 1), then the first half of the image rows shrunk: at ls = 100 the columns of the
+            # first half see nothing within ~80 log2 units of the other half's positives -> out of the f32 window
+            txt = img.clone()
+            img[: W * Bl // 2] *= 0.01
         img = img[rank * Bl:(rank + 1) * Bl].clone().requires_grad_(True)
         txt = txt[rank * Bl:(rank + 1) * Bl].clone().requires_grad_(True)
         ls = torch.tensor(case["ls"], requires_grad=True)
         crit = ClipLoss(case["local_loss"], case["gwg"], True, rank, W)
         loss = crit(img, txt, ls)["contrastive_loss"]
         loss.backward(torch.tensor(case["go"]))
-        q.put((rank, float(loss), img.grad.numpy(), txt.grad.numpy(), float(ls.grad)))
+        q.put((rank, float(loss), img.grad.numpy(), txt.grad.numpy(), float(ls.grad), list(be.calls)))
         dist.barrier()
     finally:
         dist.destroy_process_group()
+
+
+def _run_ranks(case):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, case, port, q)) for r in range(case["W"])]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=180) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    return res
+
+
+@pytest.mark.parametrize("k", [k for k, c in enumerate(RANK_CASES) if c["W"] == 2])
+def test_gloo_two_sided_forward_against_golden(k):
+    """Same golden vectors through the two-sided forward host logic: per-rank column sums gathered and merged, status
+    flag clean, predicated fallback calls skipped, text-side `v` taken from the backward launch."""
+    case = dict(RANK_CASES[k], pair=True)
+    res = _run_ranks(case)
+    Bl = case["Bl"]
+    floor = grad_floor(case["go"], case["ls"], Bl)
+    for rank, loss, di, dt, dls, calls in res:
+        gl = float(RANKS[f"c{k}_r{rank}_loss"])
+        gd = float(RANKS[f"c{k}_r{rank}_dls"])
+        gi = torch.from_numpy(RANKS[f"c{k}_r{rank}_di"]).double()
+        gt = torch.from_numpy(RANKS[f"c{k}_r{rank}_dt"]).double()
+        assert abs(loss - gl) <= 3e-6 * max(1.0, abs(gl)) + 2e-7
+        assert abs(dls - gd) <= 3e-5 * abs(gd) + 1.2e-7 * case["go"] * max(1.0, case["ls"])
+        assert float((torch.from_numpy(di).double() - gi).norm()) <= 2e-5 * float(gi.norm()) + floor
+        assert float((torch.from_numpy(dt).double() - gt).norm()) <= 2e-5 * float(gt.norm()) + floor
+        assert calls.count("pair_lse") == 1 and calls.count("merge_col_sums") == 1
+        assert calls.count("row_lse(skipped)") == 2 and calls.count("row_lse") == 0
+
+
+def test_gloo_two_sided_forward_fallback_on_out_of_window_inputs():
+    """ls = 100 and half of the global rows scaled by 0.01: the ranks whose columns fall out of the f32 window must
+    take the predicated one-sided path and every rank must still reproduce the reference (oracle rank emulation)."""
+    case = dict(W=2, Bl=48, D=512, seed=7, corr=True, ls=100.0, go=2.0, local_loss=True, gwg=True, pair=True, adv=True)
+    res = _run_ranks(case)
+    img, _ = O.make_features(2 * 48, 512, seed=7, correlated=True)
+    txt = img.clone()
+    img[:48] *= 0.01
+    ref = O.ref_port_ranks(img, txt, 100.0, 2, True, True, grad_output=2.0)
+    took_fallback = 0
+    for rank, loss, di, dt, dls, calls in res:
+        took_fallback += calls.count("row_lse") > 0
+        assert abs(loss - float(ref[rank].loss)) <= 1e-5 * abs(float(ref[rank].loss)) + 4 * 1.2e-7 * 100.0
+        floor = grad_floor(2.0, 100.0, 48)
+        assert float((torch.from_numpy(di).double() - ref[rank].d_image.double()).norm()) <= 2e-5 * float(ref[rank].d_image.norm()) + floor
+        assert float((torch.from_numpy(dt).double() - ref[rank].d_text.double()).norm()) <= 2e-5 * float(ref[rank].d_text.norm()) + floor
+    assert took_fallback >= 1
 
 
 @pytest.mark.parametrize("k", range(len(RANK_CASES)))
@@ -179,7 +239,7 @@ def test_gloo_ranks_against_golden(k):
         assert p.exitcode == 0
     Bl = case["Bl"]
     floor = grad_floor(case["go"], case["ls"], Bl)
-    for rank, loss, di, dt, dls in res:
+    for rank, loss, di, dt, dls, _calls in res:
         gl = float(RANKS[f"c{k}_r{rank}_loss"])
         gd = float(RANKS[f"c{k}_r{rank}_dls"])
         gi = torch.from_numpy(RANKS[f"c{k}_r{rank}_di"]).double()
