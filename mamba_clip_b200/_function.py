@@ -258,6 +258,7 @@ _GRAPH_WARMUP = 2
 # the static input copies / output clones of the graph path (4 x B_l x D elements) would only add traffic.
 _GRAPH_MAX_WORK = int(os.environ.get("MCLIP_GRAPH_MAX_WORK", str(1 << 37)))
 _graph_cache = {}
+_GRAPH_CACHE_MAX = 8
 
 
 def enable_cuda_graphs(flag: bool = True) -> None:
@@ -392,6 +393,8 @@ class ClipLossFunction(torch.autograd.Function):
             key = (dev.index, tuple(xi.shape), cdt, bool(local_loss), bool(gather_with_grad), int(rank), W, id(group), need_ls)
             gl = _graph_cache.get(key)
             if gl is None:
+                while len(_graph_cache) >= _GRAPH_CACHE_MAX:       # static buffers + graphs per key: keep it bounded
+                    _graph_cache.pop(next(iter(_graph_cache)))
                 gl = _graph_cache[key] = _GraphedLoss(xi, xt, (bool(local_loss), bool(gather_with_grad), int(rank), W, group), need_ls)
             gl.calls += 1
             if gl.calls > _GRAPH_WARMUP and not gl.pending:

@@ -2681,12 +2681,8 @@ Bwd2PWs bwd2p_ws_layout(int npairs, int64_t N, int64_t D, int64_t n_pad, bool ne
 // the issue thread's time waiting for TMA data, and at W = 1 the launch runs into the board power cap either way, so
 // removing the wave quantisation and the CTA prologues buys nothing yet.  Kept opt-in; passes the same parity tests.
 bool use_persistent_bwd() {
-  static int cached = -1;
-  if (cached < 0) {
-    const char* e = getenv("MCLIP_BWD_PERSIST");
-    cached = (e && e[0] == '1') ? 1 : 0;
-  }
-  return cached == 1;
+  const char* e = getenv("MCLIP_BWD_PERSIST");   // read per call: tests toggle it
+  return e && e[0] == '1';
 }
 
 // workspace carve-up shared by the size query and the launcher

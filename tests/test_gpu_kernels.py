@@ -281,6 +281,29 @@ def test_pair_forward_matches_one_sided_forward_in_the_loss():
     assert float((dt0 - dt1).norm()) <= 1e-3 * float(dt1.norm())
 
 
+@pytest.mark.parametrize("M,N,D,ls,diag_off,w", [(128, 256, 512, 14.2857, 0, (1, 1, 2)), (300, 1000, 384, 30.0, 17, (1, 1, 2)),
+                                                 (640, 768, 512, 20.0, 0, (1, 1, 2)), (512, 4096, 512, 100.0, 1024, (1, 0, 1)),
+                                                 (4096, 4096, 512, 14.2857, 0, (1, 1, 2))])
+def test_block_grad_persistent_pair_kernel(M, N, D, ls, diag_off, w, monkeypatch):
+    """MCLIP_BWD_PERSIST=1: the persistent CTA-pair kernel (pairs walk ranges of (row block, step) units, row blocks cut
+    by a range boundary go through f32 partials + fix-up) gives the same dX and rowdot as the oracle.  (640, 768) and
+    (4096, 4096) make pairs cross row-block boundaries."""
+    monkeypatch.setenv("MCLIP_BWD_PERSIST", "1")
+    be = backend(TC)
+    x, y = feats(M, N, D, torch.bfloat16, seed=M * 3 + N, correlated=True)
+    xf, yf = x.float(), y.float()
+    lse_x, _ = O.block_row_lse(xf, yf, ls, None)
+    lse_y, _ = O.block_row_lse(yf, xf, ls, None)
+    ref_dx, ref_rd = O.block_grad(xf, yf, ls, lse_x, lse_y, diag_off, *w, alpha=3.0 * ls / (2 * M))
+    dx, rd = be.block_grad(x.cuda(), y.cuda(), torch.tensor([ls], device="cuda"), torch.tensor([3.0], device="cuda"),
+                           lse_x.float().cuda(), lse_y.float().cuda() if w[1] else None, diag_off,
+                           float(w[0]), float(w[1]), float(w[2]), 1.0 / (2 * M), True)
+    torch.cuda.synchronize()
+    scale = 3.0 * ls / (2 * M) * M ** 0.5
+    assert float((dx.cpu().double() - ref_dx).norm()) <= 2e-3 * float(ref_dx.norm()) + 8 * 1.2e-7 * max(1.0, ls) * scale
+    assert float((rd.cpu().double() - ref_rd).abs().max()) <= 2e-3 * max(1.0, float(ref_rd.abs().max()))
+
+
 def load_single():
     z = np.load(os.path.join(GOLD, "single.npz"))
     return z, json.loads(str(z["cases"]))
