@@ -89,7 +89,7 @@ int mclip_pair_supported(int64_t M, int64_t N, int64_t D, int64_t ldx, int64_t l
 
 /*
  * diag[i] = <X[i], Y[i + diag_off]> (raw dot, 0 when the index is outside [0, N)) -- the positive-pair logits the
- * loss needs anyway (labels of loss.py:76-87) -- and ref[0] = max_i(logit_scale log2(e) diag[i]) - 40, the uniform
+ * loss needs anyway (labels of loss.py:76-87) -- and ref[0] = max_i(logit_scale log2(e) diag[i]) - 15, the uniform
  * exponent reference of mclip_pair_lse.  Also zeroes *status (may be NULL).  Workspace: MCLIP_OP_PAIR_REF.
  */
 int mclip_pair_ref(const void* X, const void* Y, int64_t M, int64_t N, int64_t D, int64_t ldx, int64_t ldy, int dtype,

@@ -72,7 +72,7 @@ class EmulatedPairBackend(EmulatedBackend):
         diag = torch.zeros(M, dtype=torch.float64)
         diag[ok] = (X.double()[ok] * Y.double()[idx[ok]]).sum(dim=1)
         k2 = float(ls) * LOG2E
-        c0 = float(torch.maximum(k2 * diag[ok].max(), k2 * diag[ok].min())) - 40.0 if bool(ok.any()) else 0.0
+        c0 = float(torch.maximum(k2 * diag[ok].max(), k2 * diag[ok].min())) - 15.0 if bool(ok.any()) else 0.0
         return diag.float(), torch.tensor([c0], dtype=torch.float32), torch.zeros(1, dtype=torch.int32)
 
     def pair_lse(self, X, Y, ls, ref, status, want_rowdot, col_mode=0, diag=None, diag_off=0):

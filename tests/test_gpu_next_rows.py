@@ -47,7 +47,7 @@ def test_producer_into_loss_chain_matches_fp64_chain():
     B, D, ls = 512, 512, 20.0
     g = torch.Generator().manual_seed(3)
     raw_i = torch.randn(B, D, generator=g)
-    raw_t = raw_i + 0.3 * torch.randn(B, D, generator=g)
+    raw_t = raw_i + 1.0 * torch.randn(B, D, generator=g)      # cos(pair) ~ 0.7: loss ~ 1e-3, well above the f32 floor
     a = raw_i.cuda().requires_grad_(True)
     b = raw_t.cuda().requires_grad_(True)
     loss = ClipLoss()(normalize_features(a), normalize_features(b), torch.tensor(ls, device="cuda"), output_dict=False)
@@ -62,13 +62,17 @@ def test_producer_into_loss_chain_matches_fp64_chain():
     lab = torch.arange(B)
     ref = (F.cross_entropy(logits, lab) + F.cross_entropy(logits.T, lab)) / 2
     ref.backward()
-    # the loss is ~4e-6 here (saturated softmax): one f32 ulp of an LSE of magnitude ls is the absolute floor
+    # one f32 ulp of an LSE of magnitude ls is the absolute floor of any loss value
     assert abs(float(loss.detach()) - float(ref)) <= 2e-3 * abs(float(ref)) + 1.2e-7 * ls
     # dLoss/dfeature arrives in bf16 (1.6e-3 of its norm); the normalisation backward then removes its radial
     # component, so the rounding error is relative to the *full* feature gradient while the result is only its
     # tangential part: allow the amplification |g| / |g_tangential| (the reference's AMP path rounds the same way)
-    assert O.rel_err(a.grad.cpu(), ad.grad) <= 2e-2
-    assert O.rel_err(b.grad.cpu(), bd.grad) <= 2e-2
+    # ... plus the usual absolute floor: the LSE travels from forward to backward as one f32 number of magnitude ls, so
+    # G = P_row + P_col - 2E carries ~eps*ls absolute noise (tests/test_host_logic.py `grad_floor`), here per unit-norm
+    # feature row and divided by the raw projections' norm (~sqrt(D)) by the producer
+    floor = 8 * 1.2e-7 * ls * ls / (2 * B) * B ** 0.5 / D ** 0.5
+    for got, want in ((a.grad, ad.grad), (b.grad, bd.grad)):
+        assert float((got.cpu().double() - want).norm()) <= 2e-2 * float(want.norm()) + floor
 
 
 @pytest.mark.parametrize("B,D,dtype,tol", [(64, 512, torch.float32, 1e-5), (256, 512, torch.bfloat16, 2e-3),
