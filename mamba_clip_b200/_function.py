@@ -188,8 +188,10 @@ def _forward_impl(be, xi, xt, ls, local_loss, gather_with_grad, rank, W, group, 
                 uv=uv, stats=stats, stats_work=stats_work, off=off, own_terms_only=own_terms_only)
 
 
-def _backward_impl(be, st, go, local_loss, gather_with_grad, W, group, need_i, need_t, need_ls, run=_EAGER):
-    """Everything `ClipLoss` launches in backward.  -> (d_image, d_text, d_logit_scale as a 0-dim f32 tensor)."""
+def _backward_impl(be, st, go, local_loss, gather_with_grad, W, group, need_i, need_t, need_ls, run=_EAGER, rows=None):
+    """Everything `ClipLoss` launches in backward.  -> (d_image, d_text, d_logit_scale as a 0-dim f32 tensor).
+    `rows = (lo, hi)`: only the local rows [lo, hi) need feature gradients (gradient accumulation: the other rows are
+    cached, detached features of earlier micro-batches) -- the two recompute launches shrink to that row range."""
     xi, xt, all_i, all_t, ls = st["xi"], st["xt"], st["all_i"], st["all_t"], st["ls"]
     row_lse, col_lse, diag, off = st["row_lse"], st["col_lse"], st["diag"], st["off"]
     own_terms_only = st["own_terms_only"]
@@ -223,12 +225,23 @@ def _backward_impl(be, st, go, local_loss, gather_with_grad, W, group, need_i, n
             w_row, w_col, w_diag = 1.0, 1.0, 2.0
             lse_y_i, lse_y_t = col_lse_all, row_lse_all
         d_img = d_txt = t = d_ls = v_bwd = None
-        if need_i:
-            d_img, _ = be.block_grad(xi, all_t, ls, go, row_lse, lse_y_i, off, w_row, w_col, w_diag, inv_2n, False)
-        if need_t:
-            d_txt, v_bwd = be.block_grad(xt, all_i, ls, go, col_lse, lse_y_t, off, w_row, w_col, w_diag, inv_2n, want_v)
-        elif want_v:
-            v_bwd = be.row_lse(xt, all_i, ls, off, False, True)[2]
+        if rows is not None:
+            lo, hi = rows
+            if need_i:
+                d_img, _ = be.block_grad(xi[lo:hi], all_t, ls, go, row_lse[lo:hi], lse_y_i, off + lo, w_row, w_col, w_diag,
+                                         inv_2n, False)
+            if need_t:
+                d_txt, _ = be.block_grad(xt[lo:hi], all_i, ls, go, col_lse[lo:hi], lse_y_t, off + lo, w_row, w_col, w_diag,
+                                         inv_2n, False)
+            if want_v:      # v of ALL local rows feeds d(logit_scale): one forward-only pass of the text side
+                v_bwd = be.row_lse(xt, all_i, ls, off, False, True)[2]
+        else:
+            if need_i:
+                d_img, _ = be.block_grad(xi, all_t, ls, go, row_lse, lse_y_i, off, w_row, w_col, w_diag, inv_2n, False)
+            if need_t:
+                d_txt, v_bwd = be.block_grad(xt, all_i, ls, go, col_lse, lse_y_t, off, w_row, w_col, w_diag, inv_2n, want_v)
+            elif want_v:
+                v_bwd = be.row_lse(xt, all_i, ls, off, False, True)[2]
         if need_ls:
             u, v = st["uv"]
             if v is None:
@@ -447,6 +460,59 @@ class ClipLossFunction(torch.autograd.Function):
         if d_txt is not None:
             d_txt = d_txt.to(ctx.in_dtypes[1])
         return d_img, d_txt, d_ls, None, None, None, None, None
+
+
+class ClipLossChunkFunction(torch.autograd.Function):
+    """Loss over `[cached micro-batches with rows [lo, hi) replaced by the live micro-batch]`, differentiable w.r.t. the
+    live micro-batch and `logit_scale` only.  Same forward as `ClipLossFunction` on the concatenation; the backward
+    recompute launches cover only the live rows (1/accum_freq of the work)."""
+
+    @staticmethod
+    def forward(ctx, image_j, text_j, logit_scale, image_full, text_full, lo, local_loss, gather_with_grad, rank,
+                world_size, group):
+        be = _cabi.get_backend()
+        dev = image_j.device
+        cdt = _compute_dtype(image_j)
+        hi = lo + image_j.shape[0]
+        xi = image_full.detach().to(cdt).contiguous().clone()
+        xt = text_full.detach().to(cdt).contiguous().clone()
+        xi[lo:hi] = image_j.detach().to(cdt)
+        xt[lo:hi] = text_j.detach().to(cdt)
+        if torch.is_tensor(logit_scale):
+            ls = logit_scale.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
+        else:
+            ls = torch.full((1,), float(logit_scale), dtype=torch.float32, device=dev)
+        W = int(world_size)
+        need_ls = torch.is_tensor(logit_scale) and logit_scale.requires_grad
+        st = _forward_impl(be, xi, xt, ls, bool(local_loss), bool(gather_with_grad), int(rank), W, group, need_ls)
+        loss = st.pop("loss")
+        ctx.save_for_backward(*(st.pop(k) for k in _SAVED_KEYS))
+        ctx.state = st
+        ctx.rows = (lo, hi)
+        ctx.cfg = (bool(local_loss), bool(gather_with_grad), W, group)
+        ctx.in_dtypes = (image_j.dtype, text_j.dtype)
+        ctx.ls_meta = (logit_scale.dtype, logit_scale.shape, logit_scale.device) if torch.is_tensor(logit_scale) else None
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        be = _cabi.get_backend()
+        local_loss, gather_with_grad, W, group = ctx.cfg
+        need_i, need_t, need_ls = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        need_ls = need_ls and ctx.ls_meta is not None
+        st = dict(ctx.state)
+        st.update(zip(_SAVED_KEYS, ctx.saved_tensors))
+        go = grad_out.detach().to(device=st["xi"].device, dtype=torch.float32).reshape(1).contiguous()
+        d_img, d_txt, d_ls = _backward_impl(be, st, go, local_loss, gather_with_grad, W, group, need_i, need_t, need_ls,
+                                            rows=ctx.rows)
+        if d_ls is not None:
+            dt, shape, dev = ctx.ls_meta
+            d_ls = d_ls.reshape(shape).to(device=dev, dtype=dt)
+        if d_img is not None:
+            d_img = d_img.to(ctx.in_dtypes[0])
+        if d_txt is not None:
+            d_txt = d_txt.to(ctx.in_dtypes[1])
+        return (d_img, d_txt, d_ls) + (None,) * 8
 
 
 def clip_loss(image_features: torch.Tensor, text_features: torch.Tensor, logit_scale, local_loss: bool = False,
