@@ -350,7 +350,9 @@ def main():
             "dtype": "bf16", "data": "synthetic",
             "config": dict(workload_config(B, world), **{
                        "parallelism": f"dp{world} (row/column blocks per rank, NCCL all-gather of features + LSE vectors)",
-                       "cuda_graphs": not args.no_graphs, "l2": "256 MiB flush between timed iterations", "timing": "CUDA events per step, max over ranks",
+                       "cuda_graphs": not args.no_graphs,
+                       "cuda_graphs_replayed": any(len(g.graphs) > 0 for g in mamba_clip_b200._function._graph_cache.values()),
+                       "l2": "256 MiB flush between timed iterations", "timing": "CUDA events per step, max over ranks",
                        "wall_s_timed_region": t_wall}),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * Bl * D * 2, "d2h_bytes_per_step": 4,
