@@ -217,15 +217,25 @@ class CudaBackend:
         _check(self.lib, rc, "mclip_pair_ref")
         return diag, ref, status
 
-    def pair_lse(self, X, Y, ls, ref, status, want_rowdot: bool, col_mode: int = 0, diag=None, diag_off: int = 0):
+    def pair_lse(self, X, Y, ls, ref, status, want_rowdot: bool, col_mode: int = 0, diag=None, diag_off: int = 0,
+                 out_msg: Optional[torch.Tensor] = None, out_rowdot: Optional[torch.Tensor] = None):
         """-> (row_lse [M], rowdot [M] or None, col_out [N]); ORs into `status` when the result is unusable.
-        `diag` (from pair_ref, same diag_off) is overwritten in place with the accumulator's own positive-pair dots."""
+        `diag` (from pair_ref, same diag_off) is overwritten in place with the accumulator's own positive-pair dots.
+        `out_msg` (col_mode 1 only): one caller-provided f32 buffer [N + 2 + M] that receives the column vector
+        (sums, ref, status) followed by the row LSEs -- the single message a rank all-gathers; `out_rowdot`: where to
+        put rowdot [M]."""
         dev = self._prep(X, Y, ls, ref, status)
         M, D = X.shape
         N = Y.shape[0]
-        rows = torch.empty((2, M), dtype=torch.float32, device=dev)
-        col_out = torch.empty(N + (2 if col_mode == 1 else 0), dtype=torch.float32, device=dev)
-        row_lse, rowdot = rows[0], (rows[1] if want_rowdot else None)
+        if out_msg is not None:
+            if col_mode != 1 or out_msg.numel() != N + 2 + M or out_msg.dtype != torch.float32 or not out_msg.is_contiguous():
+                raise ValueError("out_msg needs col_mode=1 and a contiguous f32 buffer of N + 2 + M elements")
+            col_out, row_lse = out_msg[:N + 2], out_msg[N + 2:]
+            rowdot = (out_rowdot if out_rowdot is not None else torch.empty(M, dtype=torch.float32, device=dev)) if want_rowdot else None
+        else:
+            rows = torch.empty((2, M), dtype=torch.float32, device=dev)
+            col_out = torch.empty(N + (2 if col_mode == 1 else 0), dtype=torch.float32, device=dev)
+            row_lse, rowdot = rows[0], (rows[1] if want_rowdot else None)
         stream = torch.cuda.current_stream(dev).cuda_stream
         ws, nws = self._workspace(M, N, D, X.dtype, OP_PAIR_LSE, dev, stream)
         with self._DeviceGuard(dev):

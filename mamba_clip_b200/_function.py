@@ -137,29 +137,48 @@ def _forward_impl(be, xi, xt, ls, local_loss, gather_with_grad, rank, W, group, 
         work_i = None
 
     # u, v: softmax-weighted raw dots (sum_j P_ij <x_i, y_j>) of the two blocks -- all d(logit_scale) needs
+    row_lse_all = col_lse_all = None      # full-length LSE vectors, when the forward already leaves them on every rank
     if getattr(be, "pair_supported", lambda *_: False)(xi, all_t):
         # two-sided forward: one pass over the rank's row block S_r = ls * I_r T_all^T gives its row LSEs and the
         # sums of every column over its rows (1 GEMM unit instead of 2).  At W > 1 the per-rank column sums are
         # all-gathered (4 * (B_g + 2) bytes per rank) and each rank finishes its own columns.  The result is
         # validated on the device; the predicated one-sided calls behind it redo the work with running maxima
         # when the status flag was raised (they exit at once otherwise -- no host sync).
-        def seg_a():
-            diag, ref, status = be.pair_ref(xi, all_t, ls, off)
-            row_lse, u, col = be.pair_lse(xi, all_t, ls, ref, status, need_ls, col_mode=0 if W == 1 else 1, diag=diag,
-                                          diag_off=off)
-            return diag, status, row_lse, u, col
-        diag, status, row_lse, u, col = run.seg("fwd_a", seg_a)
-        if W > 1:
-            parts = run.buffer("col_parts", (W, col.numel()), torch.float32, dev)      # [W, B_g + 2]
-            _gather_into(parts, col.unsqueeze(0), group, comm).wait()
+        Bg = W * Bl
+        if W == 1:
+            def seg_a():
+                diag, ref, status = be.pair_ref(xi, all_t, ls, off)
+                row_lse, u, col_lse = be.pair_lse(xi, all_t, ls, ref, status, need_ls, diag=diag, diag_off=off)
+                be.row_lse(xi, all_t, ls, off, False, need_ls, run_if=status, out_lse=row_lse, out_rowdot=u)
+                be.row_lse(xt, all_i, ls, off, False, False, run_if=status, out_lse=col_lse)
+                return diag, row_lse, u, col_lse, be.loss_finalize(row_lse, col_lse, diag, ls)
+            diag, row_lse, u, col_lse, loss = run.seg("fwd_a", seg_a)
+        else:
+            # ONE message per rank: [column sums over its rows (B_g), reference, status, its row LSEs (B_l)].  After the
+            # all-gather every rank holds everything: it finishes ALL columns itself and has every rank's row LSEs, so
+            # backward needs no further exchange.  The status words are ORed on every rank alike; if any is set, every
+            # rank redoes the full row and column statistics with the robust one-sided kernels (W x redundant, rare).
+            def seg_a():
+                diag, ref, status = be.pair_ref(xi, all_t, ls, off)
+                msg = torch.empty(Bg + 2 + Bl, dtype=torch.float32, device=dev)
+                u_all = torch.empty(Bg, dtype=torch.float32, device=dev) if need_ls else None   # only [off, off + B_l) is read
+                be.pair_lse(xi, all_t, ls, ref, status, need_ls, col_mode=1, diag=diag, diag_off=off, out_msg=msg,
+                            out_rowdot=u_all[off:off + Bl] if need_ls else None)
+                return diag, status, msg, u_all
+            diag, status, msg, u_all = run.seg("fwd_a", seg_a)
+            parts = run.buffer("col_parts", (W, Bg + 2 + Bl), torch.float32, dev)
+            _gather_into(parts, msg.unsqueeze(0), group, comm).wait()
             work_i.wait()
 
-        def seg_b():
-            col_lse = col if W == 1 else be.merge_col_sums(parts, W * Bl, off, Bl, status)
-            be.row_lse(xi, all_t, ls, off, False, need_ls, run_if=status, out_lse=row_lse, out_rowdot=u)
-            be.row_lse(xt, all_i, ls, off, False, False, run_if=status, out_lse=col_lse)
-            return col_lse, be.loss_finalize(row_lse, col_lse, diag, ls)      # the rank's local loss
-        col_lse, loss = run.seg("fwd_b", seg_b)
+            def seg_b():
+                col_all = be.merge_col_sums(parts, Bg, 0, Bg, status)
+                row_all = parts[:, Bg + 2:].reshape(-1)                      # [W, B_l] strided -> contiguous [B_g]
+                be.row_lse(all_i, all_t, ls, 0, False, need_ls, run_if=status, out_lse=row_all, out_rowdot=u_all)
+                be.row_lse(all_t, all_i, ls, 0, False, False, run_if=status, out_lse=col_all)
+                return row_all, col_all, be.loss_finalize(row_all[off:off + Bl], col_all[off:off + Bl], diag, ls)
+            row_lse_all, col_lse_all, loss = run.seg("fwd_b", seg_b)
+            row_lse, col_lse = row_lse_all[off:off + Bl], col_lse_all[off:off + Bl]
+            u = u_all[off:off + Bl] if need_ls else None
         uv = (u, None) if need_ls else None   # v comes out of the text-side backward kernel
     else:
         if work_i is not None:
@@ -180,12 +199,13 @@ def _forward_impl(be, xi, xt, ls, local_loss, gather_with_grad, rank, W, group, 
 
     own_terms_only = W > 1 and local_loss and not gather_with_grad
     stats = stats_work = None
-    if W > 1 and not own_terms_only:
+    if W > 1 and not own_terms_only and row_lse_all is None:
         # the LSE vectors of the other ranks are only needed by backward: start the gather now, wait there
         stats = run.buffer("stats", (W, 2, Bl), torch.float32, dev)
         stats_work = _gather_into(stats, torch.stack((row_lse, col_lse)).unsqueeze(0), group, comm)
     return dict(loss=loss, xi=xi, xt=xt, all_i=all_i, all_t=all_t, ls=ls, row_lse=row_lse, col_lse=col_lse, diag=diag,
-                uv=uv, stats=stats, stats_work=stats_work, off=off, own_terms_only=own_terms_only)
+                uv=uv, stats=stats, stats_work=stats_work, off=off, own_terms_only=own_terms_only,
+                row_lse_all=row_lse_all, col_lse_all=col_lse_all)
 
 
 def _backward_impl(be, st, go, local_loss, gather_with_grad, W, group, need_i, need_t, need_ls, run=_EAGER, rows=None):
@@ -213,7 +233,9 @@ def _backward_impl(be, st, go, local_loss, gather_with_grad, W, group, need_i, n
     n_ls = Bl if (W > 1 and local_loss) else Bg
 
     def seg():
-        if stats is not None:
+        if st.get("row_lse_all") is not None:        # two-sided forward at W > 1: every rank already holds both vectors
+            row_lse_all, col_lse_all = st["row_lse_all"], st["col_lse_all"]
+        elif stats is not None:
             row_lse_all = stats[:, 0, :].reshape(-1)
             col_lse_all = stats[:, 1, :].reshape(-1)
         else:

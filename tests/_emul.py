@@ -75,7 +75,7 @@ class EmulatedPairBackend(EmulatedBackend):
         c0 = float(torch.maximum(k2 * diag[ok].max(), k2 * diag[ok].min())) - 15.0 if bool(ok.any()) else 0.0
         return diag.float(), torch.tensor([c0], dtype=torch.float32), torch.zeros(1, dtype=torch.int32)
 
-    def pair_lse(self, X, Y, ls, ref, status, want_rowdot, col_mode=0, diag=None, diag_off=0):
+    def pair_lse(self, X, Y, ls, ref, status, want_rowdot, col_mode=0, diag=None, diag_off=0, out_msg=None, out_rowdot=None):
         self.calls.append("pair_lse")
         C = X.double() @ Y.double().T
         c0 = float(ref)
@@ -93,10 +93,17 @@ class EmulatedPairBackend(EmulatedBackend):
             return row_lse, rowdot, ((c0 + torch.log2(cs)) * LN2).float()
         if not bool((cs <= SUM_HI).all()):
             status |= 2
-        out = torch.empty(Y.shape[0] + 2, dtype=torch.float32)
-        out[:-2] = cs.float()
-        out[-2] = c0
-        out[-1:] = status.view(torch.float32)
+        N = Y.shape[0]
+        out = torch.empty(N + 2, dtype=torch.float32) if out_msg is None else out_msg[:N + 2]
+        out[:N] = cs.float()
+        out[N] = c0
+        out[N + 1:N + 2] = status.view(torch.float32)
+        if out_msg is not None:                       # single-message form: row LSEs ride behind the column vector
+            out_msg[N + 2:] = row_lse
+            row_lse = out_msg[N + 2:]
+            if want_rowdot and out_rowdot is not None:
+                out_rowdot.copy_(rowdot)
+                rowdot = out_rowdot
         return row_lse, rowdot, out
 
     def merge_col_sums(self, parts, n_total, col0, n, status):
