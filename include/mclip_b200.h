@@ -59,7 +59,8 @@ int mclip_workspace_bytes(int64_t M, int64_t N, int64_t D, int dtype, int op, in
  *   rowdot[i] = sum_j softmax_j(S[i, :]) * <X[i], Y[j]>       (f32; feeds d logit_scale, see mclip_dls_finalize)
  * Replaces, for one side of the loss, reference loss.py:102-111 (`logit_scale * a @ b.T`) fused with
  * the log_softmax half of F.cross_entropy at loss.py:143-144; `diag_off` is the label offset of
- * loss.py:80-81 (`labels + num_logits * rank`).  Called twice per forward: (image rows, all text) and
+ * loss.py:80-81 (`labels + num_logits * rank`).  One-sided form (the forward of fp32 inputs / D > 512, the
+ * predicated fallback behind mclip_pair_lse): called for (image rows, all text) and
  * (text rows, all image).  `logit_scale` is a device scalar (no host sync).  `diag` and `rowdot` may be NULL.
  * `run_if` (device int, may be NULL): when non-NULL and *run_if == 0 at execution time, every kernel of the call
  * exits immediately and no output is written -- this is how the robust one-sided path is chained behind

@@ -2,15 +2,18 @@
 
 The reference builds this with implicit autograd over `logit_scale * a @ b.T` and
 `F.cross_entropy` (reference src/mamba_clip/loss.py:89-113,142-145) and torch's `_AllGather`.
-Here the forward is two calls of the fused row-LSE kernel and the backward two calls of the fused
-recompute kernel; see DESIGN.md for the decomposition:
+Here (see DESIGN.md for the decomposition):
 
   rank r owns rows R of S = ls * I T^T (block "I_r x all T") and columns R of S (block "T_r x all I").
-  forward : row_lse[R] from the first block, col_lse[R] + diag from the second -> loss_r
-  exchange: features are all-gathered once (NCCL, contiguous buffers); for the modes whose gradient has
-            cross terms the two O(B) LSE vectors are all-gathered as well (8*B_l bytes per rank)
-  backward: dI_r and dT_r are each complete on the owning rank -> no gradient collective at all; only
-            `local_loss=False` needs one scalar all-reduce for d(logit_scale).
+  forward : bf16/f16, D <= 512: ONE two-sided pass over the row block gives row_lse[R] and the sums of every column over
+            the rank's rows; at W > 1 one [B_g + 2 + B_l] statistics message per rank is all-gathered and every rank
+            finishes all columns.  A device-side status flag chains the robust one-sided kernels behind it (predicated,
+            no host sync).  fp32 / D > 512: two one-sided row-LSE calls (rows R, columns R) + an all-gather of the LSEs.
+  exchange: features are all-gathered once into contiguous buffers (direct NCCL calls on the compute stream, the image
+            gather on a side stream; torch.distributed collectives as the fallback).
+  backward: two recompute launches; dI_r and dT_r are each complete on the owning rank -> no gradient collective at
+            all; only `local_loss=False` needs one scalar all-reduce for d(logit_scale).
+  launch  : eager, or -- opt-in -- CUDA-graph replay of the kernel segments between the collectives.
 Per-rank values reproduce the reference exactly, including the W x factors.
 """
 from __future__ import annotations
