@@ -23,11 +23,11 @@
 extern "C" {
 #endif
 
-#define MCLIP_ABI_VERSION 3
+#define MCLIP_ABI_VERSION 4
 
 enum { MCLIP_DTYPE_F32 = 0, MCLIP_DTYPE_BF16 = 1, MCLIP_DTYPE_F16 = 2 };
 enum { MCLIP_PATH_AUTO = 0, MCLIP_PATH_SIMT = 1, MCLIP_PATH_TCGEN05 = 2 };
-enum { MCLIP_OP_ROW_LSE = 0, MCLIP_OP_BLOCK_GRAD = 1, MCLIP_OP_PAIR_LSE = 2, MCLIP_OP_PAIR_REF = 3 };
+enum { MCLIP_OP_ROW_LSE = 0, MCLIP_OP_BLOCK_GRAD = 1, MCLIP_OP_PAIR_LSE = 2, MCLIP_OP_PAIR_REF = 3, MCLIP_OP_FUSED_GRAD = 4 };
 enum {
   MCLIP_OK = 0,
   MCLIP_ERR_INVALID = 1,      /* bad shape / pointer / alignment / enum */
@@ -132,6 +132,26 @@ int mclip_block_grad(const void* X, const void* Y, int64_t M, int64_t N, int64_t
                      int path, void* cuda_stream);
 
 /*
+ * Both feature gradients of one logits block from ONE recompute of it (the backward of reference loss.py:102-111,
+ * 142-145 at world_size 1: MmBackward x4 + LogSoftmaxBackward + NllLossBackward, 3 GEMM units instead of 4):
+ *   G_ij = exp(s_ij - lse_x[i]) + exp(s_ij - lse_y[j]) - 2 [j == i + diag_off]        s_ij = logit_scale <X[i], Y[j]>
+ *   dX   = (grad_out * logit_scale * inv_2n) * G   @ Y        [M, D] (lddx), input dtype
+ *   dY   = (grad_out * logit_scale * inv_2n) * G^T @ X        [N, D] (lddy), input dtype
+ *   xdot[i] = sum_j G_ij <X[i], Y[j]>   (f32; sum_i xdot[i] is the `t` of mclip_dls_finalize: by Euler's identity
+ *             sum_i <X[i], dL/dX[i]> = logit_scale * dL/d logit_scale, so no second statistic pass is needed)
+ * G is formed tile by tile in f16 * 2^12 exactly as in mclip_block_grad and handed from the dX pass to the dY pass
+ * through a scratch strip of `panel x N` elements inside `ws` (two strips in flight; panel ~ 4.7k rows on a B200):
+ * the M x N matrix never exists.  tcgen05 path only: bf16/f16, D % 8 == 0, D <= 512 (mclip_fused_grad_supported says
+ * whether a problem qualifies AND is large enough to profit).  Workspace: MCLIP_OP_FUSED_GRAD.  The dY pass runs on a
+ * library-owned side stream that is forked from and joined back into `cuda_stream` with events (capturable).
+ */
+int mclip_fused_grad_supported(int64_t M, int64_t N, int64_t D, int64_t ldx, int64_t ldy, int dtype);
+int mclip_fused_grad(const void* X, const void* Y, int64_t M, int64_t N, int64_t D, int64_t ldx, int64_t ldy, int dtype,
+                     const float* logit_scale, const float* grad_out, const float* lse_x, const float* lse_y,
+                     int64_t diag_off, float inv_2n, void* dX, int64_t lddx, void* dY, int64_t lddy, float* xdot, void* ws,
+                     size_t ws_bytes, void* cuda_stream);
+
+/*
  * loss = (1 / (2 n)) * sum_i (row_lse[i] + col_lse[i] - 2 * logit_scale * diag[i])
  * i.e. (CE(logits_per_image) + CE(logits_per_text)) / 2 of loss.py:142-145 for the n local samples.
  */
@@ -142,7 +162,8 @@ int mclip_loss_finalize(const float* row_lse, const float* col_lse, const float*
  * t   = sum_i (u[i] + v[i] - 2 * diag[i])            (the rank's partial of sum_ij G_ij C_ij * 2n)
  * dls = grad_out * scale * t                         (scale = 1/(2 n_ls); grad_out NULL -> 1)
  * Replaces the d(logit_scale) branch of autograd through `logit_scale * features` (loss.py:102-111).
- * Writes t_out[0] = t and dls_out[0] = dls.
+ * Writes t_out[0] = t and dls_out[0] = dls.  `v` and `diag` may be NULL (taken as 0): with u = xdot of mclip_fused_grad
+ * this finishes d(logit_scale) of the shared-recompute backward.
  */
 int mclip_dls_finalize(const float* u, const float* v, const float* diag, int64_t n, const float* grad_out,
                        float scale, float* t_out, float* dls_out, void* cuda_stream);
@@ -166,6 +187,14 @@ int mclip_normalize_rows_bwd(const float* x, const void* g, int64_t M, int64_t D
  * in *total_ms and their number in *count (either may be NULL); the record list is cleared.
  */
 int mclip_kernel_timing(int enable, float* total_ms, int* count);
+
+/*
+ * Development / measurement switches.  Read from the environment once at load time (MCLIP_BWD_PERSIST, MCLIP_FUSED_BWD,
+ * MCLIP_DBG), never on the launch path; these calls change them afterwards.  Names: "bwd_persist" (persistent variant
+ * of the CTA-pair backward kernel), "fused_bwd" (0 makes mclip_fused_grad_supported answer 0), "dbg" (profiling builds).
+ */
+int mclip_set_option(const char* name, int value);
+int mclip_get_option(const char* name, int* value);
 
 /* Number of kernel launches issued by this library on the calling thread since load (bench.py's
  * "gpu_launches" counter). */

@@ -15,10 +15,10 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmclip_b200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 DTYPE_CODES = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
 PATH_AUTO, PATH_SIMT, PATH_TCGEN05 = 0, 1, 2
-OP_ROW_LSE, OP_BLOCK_GRAD, OP_PAIR_LSE, OP_PAIR_REF = 0, 1, 2, 3
+OP_ROW_LSE, OP_BLOCK_GRAD, OP_PAIR_LSE, OP_PAIR_REF, OP_FUSED_GRAD = 0, 1, 2, 3, 4
 
 _c_f32p = ctypes.c_void_p
 _SIGNATURES = {
@@ -45,6 +45,13 @@ _SIGNATURES = {
                                         _c_f32p, _c_f32p, _c_f32p, ctypes.c_int64] + [ctypes.c_float] * 4 +
                          [ctypes.c_void_p, ctypes.c_int64, _c_f32p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
                           ctypes.c_void_p]),
+    "mclip_fused_grad_supported": (ctypes.c_int, [ctypes.c_int64] * 5 + [ctypes.c_int]),
+    "mclip_fused_grad": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int64] * 5 + [ctypes.c_int, _c_f32p,
+                                        _c_f32p, _c_f32p, _c_f32p, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p,
+                                        ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, _c_f32p, ctypes.c_void_p,
+                                        ctypes.c_size_t, ctypes.c_void_p]),
+    "mclip_set_option": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int]),
+    "mclip_get_option": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_int)]),
     "mclip_loss_finalize": (ctypes.c_int, [_c_f32p, _c_f32p, _c_f32p, ctypes.c_int64, _c_f32p, _c_f32p, ctypes.c_void_p]),
     "mclip_dls_finalize": (ctypes.c_int, [_c_f32p, _c_f32p, _c_f32p, ctypes.c_int64, _c_f32p, ctypes.c_float, _c_f32p,
                                           _c_f32p, ctypes.c_void_p]),
@@ -281,6 +288,40 @@ class CudaBackend:
         _check(self.lib, rc, "mclip_block_grad")
         return dX, rowdot
 
+    def fused_supported(self, X: torch.Tensor, Y: torch.Tensor) -> bool:
+        """True when the shared-recompute backward (both gradients from one recompute of S) can run this problem and
+        the problem is large enough to profit."""
+        if self.path == PATH_SIMT or X.dtype not in DTYPE_CODES or X.dtype == torch.float32:
+            return False
+        return bool(self.lib.mclip_fused_grad_supported(X.shape[0], Y.shape[0], X.shape[1], X.stride(0), Y.stride(0),
+                                                        DTYPE_CODES[X.dtype]))
+
+    def fused_grad(self, X, Y, ls, go, lse_x, lse_y, diag_off, inv_2n):
+        """-> (dX [M, D], dY [N, D], xdot [M]): mclip_fused_grad (weights (1, 1, 2), i.e. the full gradient)."""
+        dev = self._prep(X, Y, ls, lse_x, lse_y)
+        M, D = X.shape
+        N = Y.shape[0]
+        dX = torch.empty((M, D), dtype=X.dtype, device=dev)
+        dY = torch.empty((N, D), dtype=X.dtype, device=dev)
+        xdot = torch.empty(M, dtype=torch.float32, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        ws, nws = self._workspace(M, N, D, X.dtype, OP_FUSED_GRAD, dev, stream)
+        with self._DeviceGuard(dev):
+            rc = self.lib.mclip_fused_grad(_ptr(X), _ptr(Y), M, N, D, X.stride(0), Y.stride(0), DTYPE_CODES[X.dtype], _ptr(ls),
+                                           _ptr(go), _ptr(lse_x), _ptr(lse_y), diag_off, inv_2n, _ptr(dX), dX.stride(0),
+                                           _ptr(dY), dY.stride(0), _ptr(xdot), _ptr(ws), nws, ctypes.c_void_p(stream))
+        _check(self.lib, rc, "mclip_fused_grad")
+        return dX, dY, xdot
+
+    def set_option(self, name: str, value: int) -> None:
+        _check(self.lib, self.lib.mclip_set_option(name.encode(), int(value)), "mclip_set_option")
+        self._ws_size.clear()          # plans (and therefore workspace sizes) may depend on the switches
+
+    def get_option(self, name: str) -> int:
+        v = ctypes.c_int(0)
+        _check(self.lib, self.lib.mclip_get_option(name.encode(), ctypes.byref(v)), "mclip_get_option")
+        return v.value
+
     def loss_finalize(self, row_lse, col_lse, diag, ls):
         dev = self._prep(row_lse, col_lse, diag, ls)
         out = torch.empty((), dtype=torch.float32, device=dev)
@@ -312,6 +353,7 @@ class CudaBackend:
         return dx
 
     def dls_finalize(self, u, v, diag, go, scale):
+        """-> (t, dls); `v` / `diag` may be None (taken as zero)."""
         dev = self._prep(u, v, diag)
         out = torch.empty(2, dtype=torch.float32, device=dev)
         t_out, dls_out = out[0:1], out[1:2]
@@ -328,8 +370,13 @@ _override = None
 
 
 def set_backend_override(obj):
-    """Test hook: route the four primitive ops to `obj` (None restores the CUDA library)."""
+    """TEST-ONLY hook: route the primitive ops to `obj` (None restores the CUDA library).  The product has no CPU path;
+    tests/ install an oracle-backed stand-in to run the multi-rank host logic under gloo on CPU.  Refused unless the
+    process opted in with MCLIP_ALLOW_TEST_BACKEND=1 (tests/conftest.py sets it), so that no deployment can end up on a
+    stand-in by accident."""
     global _override
+    if obj is not None and os.environ.get("MCLIP_ALLOW_TEST_BACKEND") != "1":
+        raise RuntimeError("set_backend_override is a test hook: set MCLIP_ALLOW_TEST_BACKEND=1 (tests/conftest.py does) to use it")
     _override = obj
 
 

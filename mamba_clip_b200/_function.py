@@ -23,6 +23,7 @@ from typing import Optional, Tuple
 
 import torch
 import torch.distributed as dist
+from torch.autograd.function import once_differentiable
 
 from . import _cabi, _nccl
 
@@ -79,32 +80,6 @@ class _Done:
         return None
 
 
-_side_streams = {}
-
-
-class _StreamJoin:
-    """Work handle of a collective issued on a side stream: `wait()` makes the current stream wait for it."""
-
-    def __init__(self, stream):
-        self.stream = stream
-
-    def wait(self):
-        torch.cuda.current_stream(self.stream.device).wait_stream(self.stream)
-
-
-def _gather_on_side_stream(out, x, comm):
-    """Direct NCCL all-gather on a per-device side stream (after everything already queued on the current stream);
-    the caller's stream keeps going and joins through the returned handle."""
-    dev = x.device
-    side = _side_streams.get(dev.index)
-    if side is None:
-        side = _side_streams[dev.index] = torch.cuda.Stream(device=dev)
-    side.wait_stream(torch.cuda.current_stream(dev))
-    with torch.cuda.stream(side):
-        comm.all_gather(out, x)
-    return _StreamJoin(side)
-
-
 def _gather_into(out, x, group, comm=None):
     """All-gather into a caller-provided buffer: directly through NCCL on the current stream when a direct
     communicator exists (see _nccl.py), else through torch.distributed.  Returns a handle with `.wait()`."""
@@ -125,14 +100,18 @@ def _forward_impl(be, xi, xt, ls, local_loss, gather_with_grad, rank, W, group, 
     Bl, D = xi.shape
     dev = xi.device
     comm = _nccl.direct_comm(group, dev) if (W > 1 and dev.type == "cuda") else None
-    comm_side = _nccl.direct_comm(group, dev, slot=1) if comm is not None else None
     if W > 1:
-        # both gathers are in flight at once; the image gather (side stream / c10d's own stream) overlaps the first
-        # kernels, which only need the text features
         all_t = run.buffer("all_t", (W * Bl, D), xt.dtype, dev)
         all_i = run.buffer("all_i", (W * Bl, D), xi.dtype, dev)
-        work_t = _gather_into(all_t, xt, group, comm)
-        work_i = _gather_on_side_stream(all_i, xi, comm_side) if comm_side is not None else _gather_into(all_i, xi, group, comm)
+        if comm is not None:
+            # ONE communicator, ONE stream: both feature gathers go out as a single grouped NCCL launch on the compute
+            # stream (never two collectives of different communicators in flight on one device)
+            comm.all_gather_many(((all_t, xt), (all_i, xi)))
+            work_t = work_i = _Done
+        else:
+            # c10d: both gathers in flight on its own stream; the image gather overlaps the first kernels
+            work_t = _gather_into(all_t, xt, group, None)
+            work_i = _gather_into(all_i, xi, group, None)
         off = int(rank) * Bl
         work_t.wait()
     else:
@@ -250,6 +229,14 @@ def _backward_impl(be, st, go, local_loss, gather_with_grad, W, group, need_i, n
             w_row, w_col, w_diag = 1.0, 1.0, 2.0
             lse_y_i, lse_y_t = col_lse_all, row_lse_all
         d_img = d_txt = t = d_ls = v_bwd = None
+        if (W == 1 and rows is None and need_i and need_t and not own_terms_only
+                and getattr(be, "fused_supported", lambda *_: False)(xi, all_t)):
+            # shared-recompute backward: one recompute of S feeds dI = G T and dT = G^T I (4 GEMM units per step
+            # instead of 5); d(logit_scale) from Euler's identity sum_i <I_i, dI_i> = ls * d ls (xdot, f32 accumulators)
+            d_img, d_txt, xdot = be.fused_grad(xi, all_t, ls, go, row_lse, col_lse, off, inv_2n)
+            if need_ls:
+                t, d_ls = be.dls_finalize(xdot, None, None, go, 1.0 / (2.0 * n_ls))
+            return d_img, d_txt, t, d_ls
         if rows is not None:
             lo, hi = rows
             if need_i:
@@ -459,6 +446,7 @@ class ClipLossFunction(torch.autograd.Function):
         return loss
 
     @staticmethod
+    @once_differentiable     # the gradients come from raw kernels: a double backward must raise, not return zeros
     def backward(ctx, grad_out):
         be = _cabi.get_backend()
         local_loss, gather_with_grad, W, group = ctx.cfg
@@ -520,6 +508,7 @@ class ClipLossChunkFunction(torch.autograd.Function):
         return loss
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad_out):
         be = _cabi.get_backend()
         local_loss, gather_with_grad, W, group = ctx.cfg
@@ -538,6 +527,28 @@ class ClipLossChunkFunction(torch.autograd.Function):
         if d_txt is not None:
             d_txt = d_txt.to(ctx.in_dtypes[1])
         return (d_img, d_txt, d_ls) + (None,) * 8
+
+
+_checked_shards = set()
+
+
+def _check_equal_shards(x: torch.Tensor, group) -> None:
+    """Every rank must bring the same [B_l, D] and dtype: the flat all-gather and the fixed row offsets `rank * B_l`
+    silently corrupt (or hang) otherwise, where the reference would fail inside torch.  Checked with one tiny MIN/MAX
+    all-reduce the first time a (group, shape, dtype) is seen -- one host synchronisation per new shape, none per step."""
+    key = (id(group), tuple(x.shape), x.dtype, x.device)
+    if key in _checked_shards:
+        return
+    code = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}.get(x.dtype, 3)
+    me = torch.tensor([x.shape[0], x.shape[1], code], dtype=torch.int64)
+    dev = x.device if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    v = torch.stack((me, -me)).to(dev)
+    dist.all_reduce(v, op=dist.ReduceOp.MAX, group=group)
+    mx, mn = v[0].cpu(), -v[1].cpu()
+    if not torch.equal(mx, mn):
+        raise ValueError(f"every rank must pass features of the same shape and dtype; across the group B_l ranges over "
+                         f"[{int(mn[0])}, {int(mx[0])}], D over [{int(mn[1])}, {int(mx[1])}] (this rank: {tuple(x.shape)}, {x.dtype})")
+    _checked_shards.add(key)
 
 
 def clip_loss(image_features: torch.Tensor, text_features: torch.Tensor, logit_scale, local_loss: bool = False,
@@ -562,5 +573,6 @@ def clip_loss(image_features: torch.Tensor, text_features: torch.Tensor, logit_s
             raise ValueError(f"world_size={world_size} does not match the process group size {pg}")
         if not (0 <= int(rank) < world_size):
             raise ValueError(f"rank {rank} outside [0, {world_size})")
+        _check_equal_shards(image_features, group)
     return ClipLossFunction.apply(image_features, text_features, logit_scale, bool(local_loss),
                                   bool(gather_with_grad), int(rank), world_size, group)

@@ -11,6 +11,7 @@ MCLIP_DIRECT_NCCL=0 (or any failure to load / initialise) falls back to c10d col
 """
 from __future__ import annotations
 
+import atexit
 import ctypes
 import os
 from typing import Optional
@@ -41,8 +42,14 @@ def _load():
         lib.ncclAllGather.restype = ctypes.c_int
         lib.ncclAllGather.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p,
                                       ctypes.c_void_p]
+        lib.ncclGroupStart.restype = ctypes.c_int
+        lib.ncclGroupStart.argtypes = []
+        lib.ncclGroupEnd.restype = ctypes.c_int
+        lib.ncclGroupEnd.argtypes = []
         lib.ncclCommDestroy.restype = ctypes.c_int
         lib.ncclCommDestroy.argtypes = [ctypes.c_void_p]
+        lib.ncclCommAbort.restype = ctypes.c_int
+        lib.ncclCommAbort.argtypes = [ctypes.c_void_p]
         lib.ncclGetErrorString.restype = ctypes.c_char_p
         lib.ncclGetErrorString.argtypes = [ctypes.c_int]
         _lib = lib
@@ -84,31 +91,59 @@ class DirectComm:
                     "ncclAllGather")
 
 
-def direct_comm(group, device: torch.device, slot: int = 0) -> Optional[DirectComm]:
-    """The (cached) direct communicator number `slot` for `group` on `device`, or None when direct NCCL is disabled /
-    unavailable.  Creation is a collective: every rank of the group reaches it in its first multi-rank forward.
-    Slot 1 is a second communicator for the gather that runs on a side stream next to the first kernels (two
-    collectives of ONE communicator must not be in flight on two streams)."""
-    if os.environ.get("MCLIP_DIRECT_NCCL", "1") == "0" or device.type != "cuda":
+    def all_gather_many(self, pairs) -> None:
+        """Several all-gathers as ONE grouped NCCL operation (one launch) on the current CUDA stream."""
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self._check(self.lib.ncclGroupStart(), "ncclGroupStart")
+        try:
+            for out, x in pairs:
+                assert out.is_contiguous() and x.is_contiguous() and out.numel() * out.element_size() == self.world * x.numel() * x.element_size()
+                self._check(self.lib.ncclAllGather(ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(out.data_ptr()),
+                                                   x.numel() * x.element_size(), _NCCL_UINT8, self.comm, ctypes.c_void_p(stream)),
+                            "ncclAllGather")
+        finally:
+            self._check(self.lib.ncclGroupEnd(), "ncclGroupEnd")
+
+
+_DIRECT = os.environ.get("MCLIP_DIRECT_NCCL", "1") != "0"     # read once at import, not per step
+
+
+def direct_comm(group, device: torch.device) -> Optional[DirectComm]:
+    """The (cached) direct communicator for `group` on `device`, or None when direct NCCL is disabled / unavailable.
+    Creation is a collective: every rank of the group reaches it in its first multi-rank forward.  There is exactly ONE
+    direct communicator per (group, device) and every call on it is issued on the caller's current stream, in program
+    order -- collectives of different communicators are never in flight concurrently on a device.
+    The cache entry holds a reference to the group object, so its id cannot be reused while the entry lives."""
+    if not _DIRECT or device.type != "cuda":
         return None
     if dist.get_backend(group) != "nccl":
         return None
-    key = (id(group), device.index, slot)
-    if key not in _comms:
-        try:
-            _comms[key] = DirectComm(group, device)
-        except (OSError, AttributeError) as e:   # library not loadable: every rank fails the same way
-            import warnings
-            warnings.warn(f"mamba_clip_b200: direct NCCL unavailable ({e}); using torch.distributed collectives")
-            _comms[key] = None
-    return _comms[key]
+    pg = group if group is not None else dist.group.WORLD
+    key = (id(pg), device.index)
+    hit = _comms.get(key)
+    if hit is not None and hit[0] is pg:
+        return hit[1]
+    try:
+        comm = DirectComm(group, device)
+    except (OSError, AttributeError) as e:   # library not loadable: every rank fails the same way
+        import warnings
+        warnings.warn(f"mamba_clip_b200: direct NCCL unavailable ({e}); using torch.distributed collectives")
+        comm = None
+    _comms[key] = (pg, comm)
+    return comm
 
 
-def destroy_all() -> None:
-    for c in _comms.values():
+def destroy_all(abort: bool = False) -> None:
+    """Release every direct communicator.  Call it (collectively) before `destroy_process_group` in long-lived
+    processes that re-create groups.  At interpreter exit the registered handler uses ncclCommAbort instead, which
+    never waits for peers that may already be gone."""
+    for _, c in list(_comms.values()):
         if c is not None:
             try:
-                c.lib.ncclCommDestroy(c.comm)
+                (c.lib.ncclCommAbort if abort else c.lib.ncclCommDestroy)(c.comm)
             except Exception:
                 pass
     _comms.clear()
+
+
+atexit.register(destroy_all, True)

@@ -84,6 +84,7 @@ int mclip_workspace_bytes(int64_t M, int64_t N, int64_t D, int dtype, int op, in
   else if (op == MCLIP_OP_BLOCK_GRAD) { simt = simt_block_grad_ws(M, N, D); tc = tc_block_grad_ws(M, N, D); }
   else if (op == MCLIP_OP_PAIR_LSE) { *bytes = tc_pair_lse_ws(M, N, D); return MCLIP_OK; }
   else if (op == MCLIP_OP_PAIR_REF) { *bytes = pair_ref_ws(); return MCLIP_OK; }
+  else if (op == MCLIP_OP_FUSED_GRAD) { *bytes = tc_fused_grad_ws(M, N, D); return MCLIP_OK; }
   else { set_error("workspace_bytes: bad op %d", op); return MCLIP_ERR_INVALID; }
   if (path == MCLIP_PATH_SIMT) *bytes = simt;
   else if (path == MCLIP_PATH_TCGEN05) *bytes = tc;
@@ -180,9 +181,35 @@ int mclip_loss_finalize(const float* row_lse, const float* col_lse, const float*
   return launch_loss_finalize(row_lse, col_lse, diag, n, logit_scale, loss, (cudaStream_t)cuda_stream);
 }
 
+int mclip_fused_grad_supported(int64_t M, int64_t N, int64_t D, int64_t ldx, int64_t ldy, int dtype) {
+  return (M > 0 && N > 0 && D > 0 && tc_fused_supported(M, N, D, ldx, ldy, dtype)) ? 1 : 0;
+}
+
+int mclip_fused_grad(const void* X, const void* Y, int64_t M, int64_t N, int64_t D, int64_t ldx, int64_t ldy, int dtype,
+                     const float* logit_scale, const float* grad_out, const float* lse_x, const float* lse_y,
+                     int64_t diag_off, float inv_2n, void* dX, int64_t lddx, void* dY, int64_t lddy, float* xdot, void* ws,
+                     size_t ws_bytes, void* cuda_stream) {
+  int rc = check_common(X, Y, M, N, D, ldx, ldy, dtype, logit_scale, MCLIP_PATH_TCGEN05, "fused_grad");
+  if (rc) return rc;
+  if (!lse_x || !lse_y || !dX || !dY || !xdot) { set_error("fused_grad: null lse_x/lse_y/dX/dY/xdot"); return MCLIP_ERR_INVALID; }
+  if (lddx < D || lddy < D) { set_error("fused_grad: lddx/lddy < D"); return MCLIP_ERR_INVALID; }
+  if (!tc_supported(M, N, D, ldx | lddx, ldy | lddy, dtype, MCLIP_OP_BLOCK_GRAD) || D > 512) {
+    set_error("fused_grad: needs bf16/f16, D %% 8 == 0, D <= 512, leading dimensions %% 8 == 0");
+    return MCLIP_ERR_UNSUPPORTED;
+  }
+  const size_t need = tc_fused_grad_ws(M, N, D);
+  if (!ws || ws_bytes < need) { set_error("fused_grad: workspace %zu < %zu bytes", ws_bytes, need); return MCLIP_ERR_WORKSPACE; }
+  FusedGradArgs a{X, Y, M, N, D, ldx, ldy, dtype, logit_scale, grad_out, lse_x, lse_y, diag_off, inv_2n, dX, lddx, dY, lddy, xdot,
+                  ws, ws_bytes, (cudaStream_t)cuda_stream};
+  return tc_fused_grad(a);
+}
+
+int mclip_set_option(const char* name, int value) { return tc_set_option(name, value); }
+int mclip_get_option(const char* name, int* value) { return tc_get_option(name, value); }
+
 int mclip_dls_finalize(const float* u, const float* v, const float* diag, int64_t n, const float* grad_out,
                        float scale, float* t_out, float* dls_out, void* cuda_stream) {
-  if (!u || !v || !diag || !t_out || !dls_out || n <= 0) { set_error("dls_finalize: invalid argument"); return MCLIP_ERR_INVALID; }
+  if (!u || !t_out || !dls_out || n <= 0) { set_error("dls_finalize: invalid argument"); return MCLIP_ERR_INVALID; }
   return launch_dls_finalize(u, v, diag, n, grad_out, scale, t_out, dls_out, (cudaStream_t)cuda_stream);
 }
 

@@ -90,6 +90,24 @@ struct BlockGradArgs {
   cudaStream_t stream;
 };
 
+// shared-recompute backward: both feature gradients from ONE recompute of the logits block (tc_kernels.cu)
+struct FusedGradArgs {
+  const void* X; const void* Y;
+  int64_t M, N, D, ldx, ldy;
+  int dtype;
+  const float* logit_scale;
+  const float* grad_out;  // may be null (== 1)
+  const float* lse_x;     // [M] row LSEs
+  const float* lse_y;     // [N] column LSEs
+  int64_t diag_off;
+  float inv_2n;
+  void* dX; int64_t lddx;
+  void* dY; int64_t lddy;
+  float* xdot;            // [M] <X_i, (G Y)_i>: sums to logit_scale-free t of mclip_dls_finalize
+  void* ws; size_t ws_bytes;
+  cudaStream_t stream;
+};
+
 // SIMT (FFMA, fp32-exact) path -- simt_kernels.cu
 size_t simt_row_lse_ws(int64_t M, int64_t N, int64_t D);
 int simt_row_lse(const RowLseArgs& a);
@@ -102,6 +120,11 @@ size_t tc_row_lse_ws(int64_t M, int64_t N, int64_t D);
 int tc_row_lse(const RowLseArgs& a);
 size_t tc_block_grad_ws(int64_t M, int64_t N, int64_t D);
 int tc_block_grad(const BlockGradArgs& a);
+bool tc_fused_supported(int64_t M, int64_t N, int64_t D, int64_t ldx, int64_t ldy, int dtype);
+size_t tc_fused_grad_ws(int64_t M, int64_t N, int64_t D);
+int tc_fused_grad(const FusedGradArgs& a);
+int tc_set_option(const char* name, int value);
+int tc_get_option(const char* name, int* value);
 
 // two-sided forward -- tc_pair_lse.cu
 bool tc_pair_supported(int64_t M, int64_t N, int64_t D, int64_t ldx, int64_t ldy, int dtype);

@@ -31,7 +31,8 @@ __global__ void __launch_bounds__(256)
 simt_row_lse_kernel(const T* __restrict__ X, const T* __restrict__ Y, int64_t M, int64_t N, int64_t D,
                     int64_t ldx, int64_t ldy, const float* __restrict__ ls_ptr, int64_t diag_off,
                     int64_t cols_per_split, float* __restrict__ part_m2, float* __restrict__ part_s,
-                    float* __restrict__ part_c, float* __restrict__ diag) {
+                    float* __restrict__ part_c, float* __restrict__ diag, const int* __restrict__ run_if) {
+  if (run_if != nullptr && *run_if == 0) return;   // predicated call (mclip_row_lse): nothing is read or written
   __shared__ float Xs[kBK][kFwdBM + 1];
   __shared__ float Ys[kBK][kFwdBN + 1];
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
@@ -286,7 +287,10 @@ dls_finalize_kernel(const float* __restrict__ u, const float* __restrict__ v, co
                     float* __restrict__ dls_out) {
   float acc = 0.f;
 #pragma unroll 8
-  for (int64_t i = threadIdx.x; i < n; i += 1024) acc += (u[i] - diag[i]) + (v[i] - diag[i]);
+  for (int64_t i = threadIdx.x; i < n; i += 1024) {
+    const float d = diag ? diag[i] : 0.f;
+    acc += (u[i] - d) + ((v ? v[i] : 0.f) - d);
+  }
   const float tot = block_sum_1024(acc);
   if (threadIdx.x == 0) {
     t_out[0] = tot;
@@ -295,8 +299,16 @@ dls_finalize_kernel(const float* __restrict__ u, const float* __restrict__ v, co
 }
 
 int pick_splits(int64_t row_tiles, int64_t col_tiles) {
-  // enough CTAs for ~2 waves of 148 SMs, never more splits than column tiles
-  int64_t want = ceil_div(2 * 148, row_tiles);
+  // enough CTAs for ~2 waves of the SMs, never more splits than column tiles
+  static const int sms = [] {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) {
+      (void)cudaGetLastError();
+      n = 148;
+    }
+    return n;
+  }();
+  int64_t want = ceil_div(2 * sms, row_tiles);
   if (want < 1) want = 1;
   if (want > col_tiles) want = col_tiles;
   if (want > 64) want = 64;
@@ -320,7 +332,7 @@ int run_row_lse(const RowLseArgs& a) {
   dim3 grid((unsigned)row_tiles, (unsigned)real_splits);
   simt_row_lse_kernel<T><<<grid, 256, 0, a.stream>>>(
       reinterpret_cast<const T*>(a.X), reinterpret_cast<const T*>(a.Y), a.M, a.N, a.D, a.ldx, a.ldy,
-      a.logit_scale, a.diag_off, cols_per_split, part_m2, part_s, part_c, a.diag);
+      a.logit_scale, a.diag_off, cols_per_split, part_m2, part_s, part_c, a.diag, a.run_if);
   count_launch();
   MCLIP_CUDA_OK(cudaGetLastError());
   return launch_lse_merge(part_m2, part_s, part_c, real_splits, a.M, a.lse, a.rowdot, a.stream, a.run_if);

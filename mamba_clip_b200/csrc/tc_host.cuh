@@ -9,7 +9,14 @@ namespace mclip {
 
 // [rows, D] row-major 16-bit matrix, TMA box = [box_rows x 64 elements], 128-byte swizzle, zero fill.
 int tc_make_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t D, int64_t ld, int dtype, uint32_t box_rows);
+// [rows, cols] row-major f32 matrix, TMA box = [box_rows x box_cols] (box_cols * 4 <= 128), 128-byte swizzle.
+int tc_make_tmap_f32(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, uint32_t box_cols, uint32_t box_rows);
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device) and size high-water mark.
 int tc_set_smem(const void* kernel, uint32_t bytes);
+
+// dY_acc[N, D] (f32) += G[K, N]^T X16[K, D] (tc_gemm_tn.cu): the dY half of the shared-recompute backward.
+size_t gemm_tn_smem_bytes();
+int launch_gemm_tn(const void* G, int64_t ldg, const void* X16, int64_t ldx16, float* acc, int64_t ldacc, int64_t K,
+                   int64_t N, int64_t D, int pair_slots, cudaStream_t stream);
 
 }  // namespace mclip

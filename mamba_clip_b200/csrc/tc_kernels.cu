@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <mutex>
+#include <string>
 #include <unordered_map>
 #include <utility>
 #include <vector>
@@ -867,7 +868,6 @@ struct Bwd2Params {
 constexpr uint32_t kTile8K = 64 * 64 * 2;     // [64 rows x 64 k]
 constexpr uint32_t kStage2 = 2 * kChunkBytes; // ring stage: two [128 x 64] tiles
 constexpr int kRing2 = 4;
-constexpr int kRing3 = 3;             // the transposed kernel double-buffers G instead
 constexpr float kGScale = 4096.f;             // G is stored as G * 2^12 in f16
 
 template <bool kMasked, bool kCol>
@@ -902,9 +902,6 @@ __device__ __forceinline__ void bwd2_chunk(const uint32_t (&v)[32], uint32_t (&g
   }
 }
 
-// kPairs = 2: a cluster of four CTAs = two pairs working on adjacent 128-row blocks.  Both pairs need the same Y
-// tiles, so each CTA issues half of the TMA boxes and multicasts them to its counterpart in the other pair:
-// L2 -> SM traffic per flop halves (the pair kernel alone streams 62 B/clk/SM, at the measured L2 limit).
 // One exponential per element: P^col_ij = P^row_ij * 2^(lx2_i - ly2_j) = P^row_ij * a_i * b_j, so
 // G = P^row (1 + a_i b_j).  Only used when the caller has checked that a_i, b_j and a_i * b_j stay finite
 // (|lx2_i - ly2_j| <= 100 over the tile); otherwise bwd2_chunk evaluates both exponentials.
@@ -937,16 +934,15 @@ __device__ __forceinline__ void bwd2_chunk_fast(const uint32_t (&v)[32], uint32_
   }
 }
 
-// kGT: G is handed to the dX MMA through TMEM (TS form) instead of shared memory.  With 64 rows per CTA an SS MMA
-// fetches A (2 KB) + B (4 KB) per 64 ideal cycles = 96 B/clk, above the ~64 B/clk the tensor core sustains from
-// shared memory (measured ~100 clk per MMA); the TS form only fetches B.  For cta_group::2 with M = 128 the A rows
-// must be present in both lane halves of each CTA's TMEM ("duplicated" layout), so the epilogue exchanges the two
-// column halves of a row through a swizzled shared-memory buffer and every thread overwrites exactly the S columns
-// it loaded with the packed f16 G values.
-template <bool kBF16, int kPairs, bool kGT>
+// kStoreG: every G tile (f16 * 2^12, exactly what the dX MMA consumes) is also written to global memory with TMA
+// stores straight out of the shared-memory operand buffer (warp 3; the buffer is released by the dX commit AND the
+// store's read completion).  The panel-wise shared-recompute backward (tc_fused_grad) feeds dY = G^T X from it, so
+// that one S recompute serves both gradients.
+template <bool kBF16, bool kStoreG>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
-                      const __grid_constant__ CUtensorMap tmY16, const Bwd2Params p) {
+                      const __grid_constant__ CUtensorMap tmY16, const __grid_constant__ CUtensorMap tmG,
+                      const Bwd2Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = align1024(smem_u32(smem_raw));
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -966,21 +962,18 @@ tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   auto sread_bar = [&](int b) { return bar_base + 8u * (17 + b); };     // leader: 16 epilogue warps have loaded S(b)
   const uint32_t tmem_slot = bar_base + 8u * 19;
   uint32_t* tmem_slot_gen = reinterpret_cast<uint32_t*>(misc_gen + 8u * 19);
-  // kDeep: the S MMAs run two steps ahead of the dX MMAs (S(st+2) is issued as soon as the epilogue has pulled S(st)
+  const uint32_t gstore_bar = bar_base + 8u * 20;                        // per CTA: its 8 epilogue warps have written G
+  // The S MMAs run two steps ahead of the dX MMAs (S(st+2) is issued as soon as the epilogue has pulled S(st)
   // out of TMEM), which gives the epilogue two S durations instead of one before dX(st) needs G(st).
-  constexpr bool kDeep = !kGT;
   float* rd_scratch = reinterpret_cast<float*>(misc_gen + 256);          // [4][64]
   float* range_scratch = reinterpret_cast<float*>(misc_gen + 1280);      // [8][2]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t crank = cluster_ctarank();          // 0 .. 2*kPairs-1
-  const uint32_t rank = crank & 1;                   // role inside the pair
-  const uint32_t pr = crank >> 1;                    // pair inside the cluster
-  const uint32_t leader_rank = crank & ~1u;
+  const uint32_t rank = cluster_ctarank();           // role inside the pair
+  constexpr uint32_t leader_rank = 0;
   const bool leader = rank == 0;
-  constexpr uint16_t kAllMask = (uint16_t)((1u << (2 * kPairs)) - 1);
-  const uint16_t pair_mask = (uint16_t)(3u << (2 * pr));
-  const int64_t pair_row0 = (int64_t)(blockIdx.x / (2 * kPairs)) * (128 * kPairs) + 128 * pr;
+  constexpr uint16_t kAllMask = 3, pair_mask = 3;
+  const int64_t pair_row0 = (int64_t)(blockIdx.x / 2) * 128;
   const int64_t m0 = pair_row0 + 64 * rank;          // this CTA's 64 rows
   const int s0 = blockIdx.y * p.steps_per_split;
   const int s1 = min(p.steps_total, s0 + p.steps_per_split);
@@ -992,11 +985,13 @@ tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmY);
     tma_prefetch_desc(&tmY16);
-    for (int s = 0; s < kRing2; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), kPairs); }
+    if (kStoreG) tma_prefetch_desc(&tmG);
+    for (int s = 0; s < kRing2; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
     mbar_init(xfull_bar, 2);
     for (int b = 0; b < 2; ++b) { mbar_init(sfull_bar(b), 1); mbar_init(sread_bar(b), 2 * (kEpiThreads / 32)); }
     mbar_init(gfull_bar, 2 * (kEpiThreads / 32));
-    mbar_init(gempty_bar, 1);
+    mbar_init(gempty_bar, kStoreG ? 2 : 1);
+    mbar_init(gstore_bar, kEpiThreads / 32);
     mbar_init(dxfull_bar, 1);
     fence_barrier_init();
   } else if (warp == 2) {
@@ -1026,12 +1021,9 @@ tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         ++it;
         return (uint32_t)s;
       };
-      // one ring stage = two boxes.  kPairs == 1: this CTA loads both.  kPairs == 2: it loads box `pr` and multicasts
-      // it to the CTA with the same role in the other pair (which loads and multicasts the other box).
-      const uint16_t mc_mask = (uint16_t)((1u << rank) | (1u << (rank + 2)));
+      // one ring stage = two boxes
       auto load_box = [&](uint32_t dst, const CUtensorMap* tm, int e, int32_t c_inner, int32_t c_outer, uint32_t bar) {
-        if (kPairs == 1) tma_load_2d_cg2(dst + e * kChunkBytes, tm, c_inner, c_outer, bar);
-        else if ((uint32_t)e == pr) tma_load_2d_cg2_mc(dst + e * kChunkBytes, tm, c_inner, c_outer, bar, mc_mask);
+        tma_load_2d_cg2(dst + e * kChunkBytes, tm, c_inner, c_outer, bar);
       };
       auto load_s = [&](int st) {   // Y tiles of step st as the N operand of S: this CTA's 128 rows, all of D
         const int32_t y0 = (s0 + st) * 256 + 128 * (int32_t)rank;
@@ -1054,19 +1046,11 @@ tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
           }
         }
       };
-      if (kDeep) {
-        if (nsteps > 0) load_s(0);
-        if (nsteps > 1) load_s(1);
-        for (int st = 0; st < nsteps; ++st) {
-          if (st + 2 < nsteps) load_s(st + 2);
-          load_dx(st);
-        }
-      } else {
-        if (nsteps > 0) load_s(0);
-        for (int st = 0; st < nsteps; ++st) {
-          if (st + 1 < nsteps) load_s(st + 1);
-          load_dx(st);
-        }
+      if (nsteps > 0) load_s(0);
+      if (nsteps > 1) load_s(1);
+      for (int st = 0; st < nsteps; ++st) {
+        if (st + 2 < nsteps) load_s(st + 2);
+        load_dx(st);
       }
       if (pprof && blockIdx.x < 4 && blockIdx.y == 0)
         printf("[tma cta %d] total=%lld clk  wait_empty=%lld (per step: total %lld empty %lld)\n", (int)blockIdx.x,
@@ -1132,14 +1116,8 @@ tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
               for (int kk = 0; kk < 8; ++kk) {
                 // A = G[64 rows x 16 y] of K-chunk (2*yh + kk/4); B = Y16[16 y][128 d per CTA], MN-major
                 const uint64_t bd = make_smem_desc_sw128(b_addr + kk * 2048, kChunkBytes, 1024);
-                if (kGT) {
-                  // G(st) sits in the S buffer of this step: 8 packed columns per 16 y
-                  const uint32_t a_tmem = tmem_base + (st & 1) * 128 + (yh * 8 + kk) * 8;
-                  if (!(p.dbg & 4)) mma_ts_cg2(tmem_base + kDxCol + h * 128, a_tmem, bd, idesc_dx, (st | yh | kk) != 0);
-                } else {
-                  const uint64_t ad = make_smem_desc_sw128(g_base + (2 * yh + (kk >> 2)) * kTile8K + (kk & 3) * 32, 0, 1024);
-                  if (!(p.dbg & 4)) mma_ss_cg2(tmem_base + kDxCol + h * 128, ad, bd, idesc_dx, (st | yh | kk) != 0);
-                }
+                const uint64_t ad = make_smem_desc_sw128(g_base + (2 * yh + (kk >> 2)) * kTile8K + (kk & 3) * 32, 0, 1024);
+                if (!(p.dbg & 4)) mma_ss_cg2(tmem_base + kDxCol + h * 128, ad, bd, idesc_dx, (st | yh | kk) != 0);
               }
               mma_commit_cg2(empty_bar(s), kAllMask);
               if (yh == 1 && h == p.ndh - 1) {
@@ -1151,28 +1129,34 @@ tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
           }
         }
       };
-      if (kDeep) {
-        if (nsteps > 0) issue_s(0);
-        if (nsteps > 1) issue_s(1);
-        for (int st = 0; st < nsteps; ++st) {
-          if (st + 2 < nsteps) {
-            mbar_wait(sread_bar(st & 1), (st >> 1) & 1);   // S(st) is in registers: its TMEM buffer may be overwritten
-            tc_fence_after();
-            issue_s(st + 2);
-          }
-          issue_dx(st);
+      if (nsteps > 0) issue_s(0);
+      if (nsteps > 1) issue_s(1);
+      for (int st = 0; st < nsteps; ++st) {
+        if (st + 2 < nsteps) {
+          mbar_wait(sread_bar(st & 1), (st >> 1) & 1);   // S(st) is in registers: its TMEM buffer may be overwritten
+          tc_fence_after();
+          issue_s(st + 2);
         }
-      } else {
-        if (nsteps > 0) issue_s(0);
-        for (int st = 0; st < nsteps; ++st) {
-          if (st + 1 < nsteps) issue_s(st + 1);
-          issue_dx(st);
-        }
+        issue_dx(st);
       }
       if (prof && blockIdx.x < 4 && blockIdx.y == 0)
         printf("[mma cta %d] steps=%d total=%lld clk  wait_full=%lld  wait_gfull=%lld  (per step: total %lld full %lld gfull %lld)\n",
                (int)blockIdx.x, nsteps, clock64() - t_begin, t_full, t_gfull, (clock64() - t_begin) / max(nsteps, 1),
                t_full / max(nsteps, 1), t_gfull / max(nsteps, 1));
+    }
+  } else if (kStoreG && warp == 3) {
+    if (lane == 0) {
+      // ---------------- G store (both CTAs): shared-memory operand tiles -> global G panel ----------------
+      for (int st = 0; st < nsteps; ++st) {
+        mbar_wait(gstore_bar, st & 1);            // this CTA's 8 epilogue warps wrote G(st) and fenced it for the async proxy
+        const int32_t n0 = (s0 + st) * 256;
+#pragma unroll
+        for (int kc = 0; kc < 4; ++kc) tma_store_2d(&tmG, g_base + kc * kTile8K, n0 + 64 * kc, (int32_t)m0);
+        tma_store_commit();
+        tma_store_wait_read0();                   // the tiles have been read out of shared memory
+        mbar_arrive(gempty_bar);
+      }
+      tma_store_wait_all0();
     }
   } else if (warp >= kEpiWarp0) {
     // ---------------- epilogue: S -> G (f16 * 2^12) into shared memory; finally dX out ----------------
@@ -1241,7 +1225,7 @@ tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         uint32_t v[32];
         tmem_ld32(lane_addr + buf * 128 + half * 64 + cc * 32, v);
         tmem_ld_wait();
-        if (kDeep && cc == 1) {
+        if (cc == 1) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
@@ -1264,37 +1248,6 @@ tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
           else bwd2_chunk<false, false>(v, g[cc], k2, lx2, ly2, w_diag_s, col0, p.N, jd, rd);
         }
       }
-      if (kGT) {
-        // exchange through shared memory: row r of the buffer is 256 f16 = 32 16-byte pieces, piece index XOR (r & 7)
-        const uint32_t x_row = g_base + r * 512;
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-#pragma unroll
-          for (int pc = 0; pc < 4; ++pc) {
-            const uint32_t piece = (uint32_t)((cS >> 3) + cc * 4 + pc) ^ (uint32_t)(r & 7);
-            st_shared_v4(x_row + piece * 16, g[cc][4 * pc], g[cc][4 * pc + 1], g[cc][4 * pc + 2], g[cc][4 * pc + 3]);
-          }
-        }
-        named_bar_sync(1, kEpiThreads);      // all halves of every row are in place (and all S loads are done)
-        // this thread stores y in [128*half, 128*half + 128) of row r = 64 packed columns, over the S columns it loaded
-#pragma unroll
-        for (int blk = 0; blk < 4; ++blk) {
-          uint32_t w[16];
-#pragma unroll
-          for (int pc = 0; pc < 4; ++pc) {
-            const uint32_t piece = (uint32_t)(half * 16 + blk * 4 + pc) ^ (uint32_t)(r & 7);
-            ld_shared_v4(x_row + piece * 16, w[4 * pc], w[4 * pc + 1], w[4 * pc + 2], w[4 * pc + 3]);
-          }
-          tmem_st16(lane_addr + buf * 128 + half * 64 + blk * 16, w);
-        }
-        tmem_st_wait();
-        tc_fence_before();
-        named_bar_sync(2, kEpiThreads);      // the exchange buffer may be rewritten
-        __syncwarp();
-        if (lane == 0) {
-          if (leader) mbar_arrive(gfull_bar); else mbar_arrive_cluster(gfull_bar, leader_rank);
-        }
-      } else {
       tc_fence_before();          // TMEM reads of S are complete
       // G is single-buffered: the dX MMAs of the previous step must have finished reading it.  The values are
       // already in registers, so this wait overlaps with the S MMAs of the next step on the tensor pipe.
@@ -1312,11 +1265,11 @@ tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
           st_shared_v4(g_row + piece * 16, g[cc][4 * pc], g[cc][4 * pc + 1], g[cc][4 * pc + 2], g[cc][4 * pc + 3]);
         }
       }
-      fence_proxy_async_smem();   // G visible to the tensor-core (async) proxy
+      fence_proxy_async_smem();   // G visible to the tensor-core / TMA (async) proxy
       __syncwarp();
       if (lane == 0) {
         if (leader) mbar_arrive(gfull_bar); else mbar_arrive_cluster(gfull_bar, leader_rank);
-      }
+        if (kStoreG) mbar_arrive(gstore_bar);
       }
     }
     if (eprof && blockIdx.x < 4 && blockIdx.y == 0)
@@ -1992,448 +1945,47 @@ __global__ void bf16_to_f16_kernel(const __nv_bfloat16* __restrict__ src, int64_
   }
 }
 
-// =================================================================================================
-// backward, transposed CTA-pair version (D <= 512): both MMAs math-bound
-// =================================================================================================
-// Measured on B200: a tcgen05.mma fetches its B operand from shared memory at ~42 B/clk, so an instruction is
-// B-bound unless M per CTA >= ~98 rows -- the pair kernel above (64 X rows per CTA, B = 128 Y rows) runs ~100 clk
-// per MMA instead of 64.  Here the roles are swapped so that the small operand is B:
-//   S^T  = Y X^T        M = 256 (y: 128 per CTA)  N = 128 (x: 64 per CTA, resident)   -> [128 y x 128 x] per CTA
-//   dX^T += Y16^T G^T   M = 256 (d: 128 per CTA, MN-major A)  N = 128 (x)  K = 256 (y) -> [128 d x 128 x] x 2 halves of D
-// TMEM use is unchanged (2 x 128 + 256 columns).  The epilogue holds y on lanes, so a thread produces one row
-// G^T[y, 64 x] = one 128-byte line of the B operand [K = y][N = x].  The K dimension (y) of dX^T spans both CTAs,
-// while the N split gives CTA r the x half r: the warpgroup whose x half belongs to the peer writes its lines
-// straight into the peer's shared memory (st.shared::cluster) -- 16 KB per step and CTA.
-struct Bwd3Params {
-  int64_t M, N, D;
-  int kpairs, ndh, steps_total, steps_per_split, nsplit;
-  int64_t diag_off;
-  const float* ls;
-  const float* go;
-  const float* lx2;     // [m_pad] lse_x in log2 units, row weight and G scale folded, +inf padded
-  const float* bx;      // [m_pad] 2^(mu0 - lx2[x]) (0 in the padding)
-  const float* xmm;     // [m_pad / 128][2] min / max of lx2 per 128-row block
-  const float* ly2;     // [n_pad] lse_y in log2 units, column weight and G scale folded, +inf padded (null: no column term)
-  const float* ymm;     // [n_pad / 128][2]
-  const float* mu0;     // [1]
-  float w_diag, inv_2n;
-  int has_col;
-  void* dX;
-  int64_t lddx;
-  float* acc_ws;
-  int dbg;
-};
-
-// mode: 0 = one exponential (P^col and the separable factor), 1 = two exponentials, 2 = row term only
-template <int kMode, bool kMasked>
-__device__ __forceinline__ void bwd3_chunk(const uint32_t (&v)[32], uint32_t (&g)[16], float k2, float ly, float a_y,
-                                           const float* __restrict__ xarr, float w_diag_s, int xd, bool y_ok) {
-  float xa[32];   // kMode 0: b_x, else lx2[x]
-#pragma unroll
-  for (int j = 0; j < 32; j += 4) {
-    const float4 t = __ldg(reinterpret_cast<const float4*>(xarr + j));
-    xa[j] = t.x; xa[j + 1] = t.y; xa[j + 2] = t.z; xa[j + 3] = t.w;
-  }
-#pragma unroll
-  for (int j = 0; j < 32; j += 2) {
-    float gv[2];
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const float c = __uint_as_float(v[j + e]);
-      float gg;
-      if (kMode == 0) gg = ex2_approx(fmaf(c, k2, -ly)) * fmaf(a_y, xa[j + e], 1.f);
-      else if (kMode == 1) gg = ex2_approx(fmaf(c, k2, -ly)) + ex2_approx(fmaf(c, k2, -xa[j + e]));
-      else gg = ex2_approx(fmaf(c, k2, -xa[j + e]));
-      if (kMasked) {
-        if (j + e == xd) gg -= w_diag_s;
-        if (!y_ok) gg = 0.f;
-      }
-      gv[e] = gg;
-    }
-    g[j >> 1] = pack_f16x2(gv[0], gv[1]);
-  }
-}
-
-template <bool kBF16>
-__global__ void __launch_bounds__(kThreads, 1)
-tc_block_grad3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
-                      const __grid_constant__ CUtensorMap tmY16, const Bwd3Params p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = align1024(smem_u32(smem_raw));
-  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t x_base = smem_base;                              // [8][64 x rows][64 k]          64 KB
-  const uint32_t g_base = x_base + 8 * kTile8K;                   // [2][256 y][64 x] f16, MN-major 64 KB (double buffer)
-  const uint32_t ring_base = g_base + 8 * kTile8K;                // [kRing3][2][128][64]           96 KB
-  const uint32_t misc_base = ring_base + kRing3 * kStage2;
-  uint8_t* misc_gen = smem_gen + (misc_base - smem_base);
-  const uint32_t bar_base = misc_base;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };             // leader: both CTAs' TMA bytes
-  auto empty_bar = [&](int s) { return bar_base + 8u * (4 + s); };      // per CTA, MMA commit multicast
-  const uint32_t xfull_bar = bar_base + 8u * 8;                          // leader
-  auto sfull_bar = [&](int b) { return bar_base + 8u * (9 + b); };      // per CTA, multicast
-  auto gfull_bar = [&](int b) { return bar_base + 8u * (11 + b); };     // leader: 16 epilogue warps
-  auto gempty_bar = [&](int b) { return bar_base + 8u * (13 + b); };    // per CTA, multicast
-  const uint32_t dxfull_bar = bar_base + 8u * 15;                        // per CTA, multicast
-  const uint32_t tmem_slot = bar_base + 8u * 16;
-  uint32_t* tmem_slot_gen = reinterpret_cast<uint32_t*>(misc_gen + 8u * 16);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const bool leader = rank == 0;
-  const int64_t pair_row0 = (int64_t)(blockIdx.x >> 1) * 128;        // the pair's 128 x rows
-  const int s0 = blockIdx.y * p.steps_per_split;
-  const int s1 = min(p.steps_total, s0 + p.steps_per_split);
-  const int nsteps = s1 - s0;
-  constexpr uint32_t kTmemCols = 512;
-  constexpr uint32_t kDxCol = 256;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmX);
-    tma_prefetch_desc(&tmY);
-    tma_prefetch_desc(&tmY16);
-    for (int s = 0; s < kRing3; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
-    mbar_init(xfull_bar, 2);
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(sfull_bar(b), 1);
-      mbar_init(gfull_bar(b), 2 * (kEpiThreads / 32));
-      mbar_init(gempty_bar(b), 1);
-    }
-    mbar_init(dxfull_bar, 1);
-    fence_barrier_init();
-  } else if (warp == 2) {
-    tmem_alloc_cg2(tmem_slot, kTmemCols);
-    tmem_relinquish_cg2();
-  }
-  tc_fence_before();
-  cluster_sync_all();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_gen;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      // ---------------- TMA producer (both CTAs) ----------------
-      // X: this CTA's 64 rows of the pair's block (the N operand of S^T), all of D, resident
-      if (leader) mbar_expect_tx(xfull_bar, 2 * 8 * kTile8K); else mbar_arrive_cluster(xfull_bar, 0);
-      for (int c = 0; c < 8; ++c)
-        tma_load_2d_cg2(x_base + c * kTile8K, &tmX, c * 64, (int32_t)(pair_row0 + 64 * rank), xfull_bar);
-      uint32_t it = 0;
-      auto stage_begin = [&]() -> uint32_t {
-        const int s = it % kRing3;
-        const uint32_t ph = (it / kRing3) & 1;
-        mbar_wait(empty_bar(s), ph ^ 1);
-        if (leader) mbar_expect_tx(full_bar(s), 2 * kStage2); else mbar_arrive_cluster(full_bar(s), 0);
-        ++it;
-        return (uint32_t)s;
-      };
-      auto load_s = [&](int st) {   // Y rows of this CTA's half of the step (the M operand of S^T), all of D
-        const int32_t y0 = (s0 + st) * 256 + 128 * (int32_t)rank;
-        for (int i = 0; i < p.kpairs; ++i) {
-          const uint32_t s = stage_begin();
-          const uint32_t dst = ring_base + s * kStage2;
-          tma_load_2d_cg2(dst, &tmY, (2 * i) * 64, y0, full_bar(s));
-          tma_load_2d_cg2(dst + kChunkBytes, &tmY, (2 * i + 1) * 64, y0, full_bar(s));
-        }
-      };
-      auto load_dx = [&](int st) {  // Y16[y half][this CTA's 128 d of half h]: the MN-major M operand of dX^T
-        for (int yh = 0; yh < 2; ++yh) {
-          const int32_t y0 = (s0 + st) * 256 + 128 * yh;
-          for (int h = 0; h < p.ndh; ++h) {
-            const uint32_t s = stage_begin();
-            const uint32_t dst = ring_base + s * kStage2;
-            const int32_t dcol = (4 * h + 2 * (int32_t)rank) * 64;
-            tma_load_2d_cg2(dst, &tmY16, dcol, y0, full_bar(s));
-            tma_load_2d_cg2(dst + kChunkBytes, &tmY16, dcol + 64, y0, full_bar(s));
-          }
-        }
-      };
-      if (nsteps > 0) load_s(0);
-      for (int st = 0; st < nsteps; ++st) {
-        if (st + 1 < nsteps) load_s(st + 1);
-        load_dx(st);
-      }
-    }
-  } else if (warp == 1) {
-    if (leader) {
-      // ---------------- MMA issuer (leader CTA only): the whole warp waits, one elected lane issues ----------------
-      const bool elected = elect_one();
-      const uint32_t idesc_s = make_idesc_f16(kBF16, kBF16, 256, 128, false, false);
-      const uint32_t idesc_dx = make_idesc_f16(false, false, 256, 128, true, true);
-      mbar_wait(xfull_bar, 0);
-      uint32_t it = 0;
-      const bool prof = kProfile && (p.dbg & 16) != 0 && elected;
-      long long t_full = 0, t_gfull = 0, t_begin = clock64();
-      auto stage_wait = [&]() -> uint32_t {
-        const int s = it % kRing3;
-        const uint32_t ph = (it / kRing3) & 1;
-        const long long t0 = prof ? clock64() : 0;
-        mbar_wait(full_bar(s), ph);
-        if (prof) t_full += clock64() - t0;
-        tc_fence_after();
-        ++it;
-        return (uint32_t)s;
-      };
-      auto issue_s = [&](int st) {
-        const uint32_t d_tmem = tmem_base + (st & 1) * 128;
-        for (int i = 0; i < p.kpairs; ++i) {
-          const uint32_t s = stage_wait();
-          const uint32_t a_addr = ring_base + s * kStage2;
-          if (elected) {
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint64_t ad = make_smem_desc_sw128(a_addr + e * kChunkBytes + k * 32, 0, 1024);       // Y [128 y][64 k]
-                const uint64_t bd = make_smem_desc_sw128(x_base + (2 * i + e) * kTile8K + k * 32, 0, 1024);  // X [64 x][64 k]
-                mma_ss_cg2(d_tmem, ad, bd, idesc_s, (i | e | k) != 0);
-              }
-            }
-            mma_commit_cg2(empty_bar(s), 3);
-            if (i == p.kpairs - 1) mma_commit_cg2(sfull_bar(st & 1), 3);
-          }
-          __syncwarp();
-        }
-      };
-      auto issue_dx = [&](int st) {
-        {
-          const long long t0 = prof ? clock64() : 0;
-          mbar_wait_acquire_cluster(gfull_bar(st & 1), (st >> 1) & 1);
-          if (prof) t_gfull += clock64() - t0;
-        }
-        tc_fence_after();
-        for (int yh = 0; yh < 2; ++yh) {
-          for (int h = 0; h < p.ndh; ++h) {
-            const uint32_t s = stage_wait();
-            const uint32_t a_addr = ring_base + s * kStage2;
-            if (elected) {
-#pragma unroll
-              for (int kk = 0; kk < 8; ++kk) {
-                // A = Y16^T: [M = 128 d per CTA (two 64-wide atoms, kChunkBytes apart)][K = 16 y], MN-major
-                // B = G^T:   [N = 64 x per CTA (one atom)][K = 16 y], MN-major, rows (yh*8 + kk)*16 .. of the G tile
-                const uint64_t ad = make_smem_desc_sw128(a_addr + kk * 2048, kChunkBytes, 1024);
-                const uint64_t bd = make_smem_desc_sw128(g_base + (st & 1) * (4 * kTile8K) + (yh * 8 + kk) * 2048, 0, 1024);
-                mma_ss_cg2(tmem_base + kDxCol + h * 128, ad, bd, idesc_dx, (st | yh | kk) != 0);
-              }
-              mma_commit_cg2(empty_bar(s), 3);
-              if (yh == 1 && h == p.ndh - 1) {
-                mma_commit_cg2(gempty_bar(st & 1), 3);
-                if (st == nsteps - 1) mma_commit_cg2(dxfull_bar, 3);
-              }
-            }
-            __syncwarp();
-          }
-        }
-      };
-      if (nsteps > 0) issue_s(0);
-      for (int st = 0; st < nsteps; ++st) {
-        if (st + 1 < nsteps) issue_s(st + 1);
-        issue_dx(st);
-      }
-      if (prof && blockIdx.x < 2 && blockIdx.y == 0)
-        printf("[mma3 cta %d] steps=%d total=%lld clk wait_full=%lld wait_gfull=%lld (per step: total %lld full %lld gfull %lld)\n",
-               (int)blockIdx.x, nsteps, clock64() - t_begin, t_full, t_gfull, (clock64() - t_begin) / max(nsteps, 1),
-               t_full / max(nsteps, 1), t_gfull / max(nsteps, 1));
-    }
-  } else if (warp >= kEpiWarp0) {
-    // ---------------- epilogue: S^T -> G^T rows (f16 * 2^12) into the owner's G tile; finally dX^T out ----------------
-    const int ew = warp - kEpiWarp0;
-    const int q = warp & 3;                   // TMEM lane quadrant
-    const int half = ew >> 2;                 // x half handled by this warpgroup = CTA that consumes it as B operand
-    const int yl = q * 32 + lane;             // y row within this CTA's 128 (TMEM lane)
-    const float ls = p.ls[0];
-    const float k2 = ls * kLog2e;
-    const bool has_col = p.has_col != 0;
-    const float w_diag_s = p.w_diag * kGScale;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    const int64_t xg0 = pair_row0 + half * 64;             // first global x of this thread's columns
-    // destination of this thread's G line: row (128 * rank + yl) of the G tile in CTA `half`
-    const uint32_t grow = (uint32_t)(128 * rank + yl);
-    const uint32_t g_line_local = g_base + grow * 128;
-    const bool remote = (uint32_t)half != rank;
-    const uint32_t g_line0 = remote ? map_to_cta(g_line_local, (uint32_t)half) : g_line_local;   // + buf * 32 KB
-    float mu0 = 0.f, x_min = 0.f, x_max = 0.f;
-    if (has_col) {
-      mu0 = p.mu0[0];
-      const float2 xm = __ldg(reinterpret_cast<const float2*>(p.xmm) + (blockIdx.x >> 1));
-      x_min = xm.x; x_max = xm.y;
-    }
-    const bool x_ok = has_col && fabsf(x_min - mu0) <= 120.f && fabsf(x_max - mu0) <= 120.f;
-    for (int st = 0; st < nsteps; ++st) {
-      const int buf = st & 1;
-      const uint32_t bph = (st >> 1) & 1;
-      const int64_t n0 = (int64_t)(s0 + st) * 256 + 128 * rank;      // first y of this CTA in this step
-      const int64_t yg = n0 + yl;
-      const bool y_ok = yg < p.N;
-      float ly = INFINITY, a_y = 0.f;
-      bool fast = false;
-      if (has_col) {
-        ly = __ldg(p.ly2 + yg);                                        // +inf in the padding -> P^col = 0
-        const float2 ym = __ldg(reinterpret_cast<const float2*>(p.ymm) + ((s0 + st) * 2 + (int)rank));
-        fast = x_ok && !(p.dbg & 8) && (ym.y - x_min <= 100.f) && (x_max - ym.x <= 100.f) &&
-               (!(ym.x <= ym.y) || (fabsf(ym.x - mu0) <= 120.f && fabsf(ym.y - mu0) <= 120.f));
-        if (fast) a_y = y_ok ? ex2_approx(ly - mu0) : 0.f;
-      }
-      mbar_wait(sfull_bar(buf), bph);
-      tc_fence_after();
-      // diagonal of this pair's rows: x_global + diag_off == y_global
-      const int64_t xdg = yg - p.diag_off - xg0;     // column (within this thread's 64) holding this row's positive
-      const bool special = (n0 + 128 > p.N) || (n0 + 128 > pair_row0 + p.diag_off && n0 < pair_row0 + p.diag_off + 128);
-      uint32_t g[2][16];
-#pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        uint32_t v[32];
-        tmem_ld32(lane_addr + buf * 128 + half * 64 + cc * 32, v);
-        tmem_ld_wait();
-        const int xd = (xdg >= cc * 32 && xdg < cc * 32 + 32) ? (int)(xdg - cc * 32) : -1;
-        const float* xarr = (fast ? p.bx : p.lx2) + xg0 + cc * 32;
-        if (!has_col) {
-          if (special) bwd3_chunk<2, true>(v, g[cc], k2, ly, a_y, xarr, w_diag_s, xd, y_ok);
-          else bwd3_chunk<2, false>(v, g[cc], k2, ly, a_y, xarr, w_diag_s, xd, y_ok);
-        } else if (fast) {
-          if (special) bwd3_chunk<0, true>(v, g[cc], k2, ly, a_y, xarr, w_diag_s, xd, y_ok);
-          else bwd3_chunk<0, false>(v, g[cc], k2, ly, a_y, xarr, w_diag_s, xd, y_ok);
-        } else {
-          if (special) bwd3_chunk<1, true>(v, g[cc], k2, ly, a_y, xarr, w_diag_s, xd, y_ok);
-          else bwd3_chunk<1, false>(v, g[cc], k2, ly, a_y, xarr, w_diag_s, xd, y_ok);
-        }
-      }
-      tc_fence_before();          // TMEM reads of S^T are complete
-      // G tile `buf` was last read by dX of step st-2 (in both CTAs): long done in steady state
-      mbar_wait(gempty_bar(buf), bph ^ 1);
-      const uint32_t g_line = g_line0 + buf * (4 * kTile8K);
-#pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-#pragma unroll
-        for (int pc = 0; pc < 4; ++pc) {
-          const uint32_t piece = (uint32_t)((cc * 4 + pc) ^ (grow & 7));
-          if (remote) st_cluster_v4(g_line + piece * 16, g[cc][4 * pc], g[cc][4 * pc + 1], g[cc][4 * pc + 2], g[cc][4 * pc + 3]);
-          else st_shared_v4(g_line + piece * 16, g[cc][4 * pc], g[cc][4 * pc + 1], g[cc][4 * pc + 2], g[cc][4 * pc + 3]);
-        }
-      }
-      // generic-proxy stores (local or peer shared memory) -> tensor-core (async) proxy
-      if (p.dbg & 32) fence_proxy_async_all();
-      else if (remote) fence_proxy_async_smem_cluster();
-      else fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_release_cluster(gfull_bar(buf), 0, !leader);
-    }
-    // ---- dX^T accumulator -> global: lane = d, columns = x ----
-    mbar_wait(dxfull_bar, 0);
-    tc_fence_after();
-    const float alpha = (p.go ? p.go[0] : 1.f) * ls * p.inv_2n * (1.f / kGScale);
-    for (int h = 0; h < p.ndh; ++h) {
-      const int64_t d = (int64_t)h * 256 + 128 * rank + yl;
-#pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
-        uint32_t v[32];
-        tmem_ld32(lane_addr + kDxCol + h * 128 + half * 64 + cc * 32, v);
-        tmem_ld_wait();
-        if (d < p.D && nsteps > 0) {
-          const int64_t x0 = xg0 + cc * 32;
-          if (p.nsplit > 1) {
-            float* dst = p.acc_ws + ((int64_t)blockIdx.y * p.M + x0) * p.D + d;
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (x0 + j < p.M) dst[(int64_t)j * p.D] = __uint_as_float(v[j]);
-          } else {
-            uint16_t* dst = reinterpret_cast<uint16_t*>(p.dX) + x0 * p.lddx + d;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (x0 + j < p.M) {
-                const uint32_t pk = kBF16 ? pack_bf16x2(__uint_as_float(v[j]) * alpha, 0.f)
-                                          : pack_f16x2(__uint_as_float(v[j]) * alpha, 0.f);
-                dst[(int64_t)j * p.lddx] = (uint16_t)(pk & 0xFFFFu);
-              }
-            }
-          }
-        }
-      }
-    }
-  }
-
-  tc_fence_before();
-  cluster_sync_all();
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc_cg2(tmem_base, kTmemCols);
-  }
-}
-
-// Row / column statistics for the transposed backward kernel (one block of 1024 threads), log2 units:
-//   lx2[x] = lse_x[x] * log2e - lw_row (+inf padded to m_pad), bx[x] = 2^(mu0 - lx2[x]) (0 padded), xmm per 128 rows
-//   ly2[y] = lse_y[y] * log2e - lw_col (+inf padded to n_pad), ymm per 128 rows;  mu0 = midpoint of the lx2 range
-__global__ void __launch_bounds__(1024)
-prep_bwd3_kernel(const float* __restrict__ lse_x, int64_t M, int64_t m_pad, float lw_row, const float* __restrict__ lse_y,
-                 int64_t N, int64_t n_pad, float lw_col, float* __restrict__ lx2, float* __restrict__ bx,
-                 float* __restrict__ xmm, float* __restrict__ ly2, float* __restrict__ ymm, float* __restrict__ mu0_out) {
-  __shared__ float red_min[32], red_max[32];
-  __shared__ float mu_s;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float mn = INFINITY, mx = -INFINITY;
-  for (int64_t j = tid; j < M; j += 1024) {
-    const float v = lse_x[j] * kLog2e - lw_row;
-    mn = fminf(mn, v); mx = fmaxf(mx, v);
-  }
-#pragma unroll
-  for (int o = 16; o >= 1; o >>= 1) {
-    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  }
-  if (lane == 0) { red_min[warp] = mn; red_max[warp] = mx; }
-  __syncthreads();
-  if (warp == 0) {
-    mn = red_min[lane]; mx = red_max[lane];
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) {
-      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    }
-    if (lane == 0) { mu_s = 0.5f * mn + 0.5f * mx; mu0_out[0] = mu_s; }
-  }
-  __syncthreads();
-  const float mu = mu_s;
-  // 128-row blocks of x and of y, one warp per block (4 elements per lane)
-  const int64_t xb = m_pad / 128, yb = lse_y ? n_pad / 128 : 0;
-  for (int64_t b = warp; b < xb + yb; b += 32) {
-    const bool is_x = b < xb;
-    const int64_t base = (is_x ? b : b - xb) * 128;
-    const float* src = is_x ? lse_x : lse_y;
-    const int64_t lim = is_x ? M : N;
-    const float lw = is_x ? lw_row : lw_col;
-    float smn = INFINITY, smx = -INFINITY;
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int64_t j = base + e * 32 + lane;
-      const bool ok = j < lim;
-      const float v = ok ? src[j] * kLog2e - lw : INFINITY;
-      if (is_x) { lx2[j] = v; bx[j] = ok ? exp2f(mu - v) : 0.f; }
-      else ly2[j] = v;
-      if (ok) { smn = fminf(smn, v); smx = fmaxf(smx, v); }
-    }
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) {
-      smn = fminf(smn, __shfl_xor_sync(0xffffffffu, smn, o));
-      smx = fmaxf(smx, __shfl_xor_sync(0xffffffffu, smx, o));
-    }
-    if (lane == 0) {
-      float* dst = is_x ? xmm + 2 * b : ymm + 2 * (b - xb);
-      dst[0] = smn; dst[1] = smx;
-    }
-  }
-}
-
 // ---- host side ----------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-// MCLIP_BWD_1CTA=1 forces the single-CTA backward kernel also for D <= 512 (development A/B switch).
-bool use_single_cta_bwd() {
-  static int cached = -1;
-  if (cached < 0) {
-    const char* e = getenv("MCLIP_BWD_1CTA");
-    cached = (e && e[0] == '1') ? 1 : 0;
+// Development switches are read from the environment ONCE, when the library is loaded (never on the launch path), and
+// can be changed afterwards through mclip_set_option (tests do that instead of re-reading the environment).
+struct Options {
+  int bwd_persist;   // MCLIP_BWD_PERSIST: persistent CTA-pair backward kernel (stream-K vehicle)
+  int dbg;           // MCLIP_DBG: development masks; only honoured by -DMCLIP_PROFILE builds
+  int fused_bwd;     // MCLIP_FUSED_BWD: shared-recompute backward (one S recompute for dX and dY) where it applies
+  Options() {
+    auto geti = [](const char* k, int dflt) { const char* e = getenv(k); return e ? atoi(e) : dflt; };
+    bwd_persist = geti("MCLIP_BWD_PERSIST", 0);
+    dbg = kProfile ? geti("MCLIP_DBG", 0) : 0;
+    fused_bwd = geti("MCLIP_FUSED_BWD", 1);
   }
-  return cached == 1;
+};
+Options& options() {
+  static Options o;
+  return o;
+}
+
+// SM count of the current device (cudaDeviceProp, cached per device); a CTA pair occupies two SMs.
+int sm_count() {
+  static std::mutex mu;
+  static std::unordered_map<int, int> cache;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(dev);
+  if (it != cache.end()) return it->second;
+  int n = 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 2) { (void)cudaGetLastError(); n = 148; }
+  cache[dev] = n;
+  return n;
+}
+int pair_slots() { return sm_count() / 2; }
+unsigned ew_blocks(int64_t work_items, int per_block) {   // grid of an elementwise helper: at most 8 blocks per SM
+  const int64_t want = ceil_div(work_items, per_block), cap = (int64_t)sm_count() * 8;
+  return (unsigned)(want < cap ? want : cap);
 }
 
 // Driver-API calls (cuTensorMapEncodeTiled) need the primary context bound to the calling thread; autograd's
@@ -2498,7 +2050,7 @@ FwdPlan plan_fwd(int64_t M, int64_t N, int64_t D) {
   f.stages = st > (int)kMaxStages ? (int)kMaxStages : st;
   f.tiles_total = (int)ceil_div(N, f.bn);
   const int64_t m_tiles = ceil_div(M, 128);
-  // splits: fill the 148 SMs, prefer wave counts that quantise well, never more than the tiles
+  // splits: fill the SMs, prefer wave counts that quantise well, never more than the tiles
   int best = 1;
   double best_cost = 1e30;
   const int max_split = f.tiles_total < 64 ? f.tiles_total : 64;
@@ -2507,7 +2059,7 @@ FwdPlan plan_fwd(int64_t M, int64_t N, int64_t D) {
     const int real = (int)ceil_div(f.tiles_total, tps);
     if (real != s) continue;
     const int64_t ctas = m_tiles * s;
-    const double waves = (double)ceil_div(ctas, 148);
+    const double waves = (double)ceil_div(ctas, sm_count());
     const double cost = waves * (tps + 1.5);  // +1.5 tile-times of per-CTA prologue (X load, TMEM alloc, drain)
     if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
   }
@@ -2517,17 +2069,7 @@ FwdPlan plan_fwd(int64_t M, int64_t N, int64_t D) {
   return f;
 }
 
-// MCLIP_FWD_1CTA=1 forces the single-CTA forward kernel also for D <= 512 (development A/B switch).
-bool use_single_cta_fwd() {
-  static int cached = -1;
-  if (cached < 0) {
-    const char* e = getenv("MCLIP_FWD_1CTA");
-    cached = (e && e[0] == '1') ? 1 : 0;
-  }
-  return cached == 1;
-}
-
-bool fwd_uses_pair(int64_t D) { return D <= 512 && !use_single_cta_fwd(); }
+bool fwd_uses_pair(int64_t D) { return D <= 512; }
 
 FwdPlan plan_fwd2(int64_t M, int64_t N, int64_t D) {
   FwdPlan f;
@@ -2544,7 +2086,7 @@ FwdPlan plan_fwd2(int64_t M, int64_t N, int64_t D) {
     const int tps = (int)ceil_div(f.tiles_total, s);
     const int real = (int)ceil_div(f.tiles_total, tps);
     if (real != s) continue;
-    const double waves = (double)ceil_div(pairs * s, 74);
+    const double waves = (double)ceil_div(pairs * s, pair_slots());
     const double cost = waves * (tps + 1.5);
     if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
   }
@@ -2575,7 +2117,7 @@ BwdPlan plan_bwd(int64_t M, int64_t N, int64_t D) {
     const int sps = (int)ceil_div(b.steps_total, s);
     const int real = (int)ceil_div(b.steps_total, sps);
     if (real != s) continue;
-    const double waves = (double)ceil_div(items * s, 148);
+    const double waves = (double)ceil_div(items * s, sm_count());
     const double cost = waves * (sps + 3.0) + (s > 1 ? 0.02 * b.steps_total : 0.0);
     if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
   }
@@ -2585,40 +2127,19 @@ BwdPlan plan_bwd(int64_t M, int64_t N, int64_t D) {
   return b;
 }
 
-struct Bwd2Plan { int kch; int kpairs; int ndh; int steps_total; int nsplit; int steps_per_split; uint32_t smem; int cpairs; };
+struct Bwd2Plan { int kch; int kpairs; int ndh; int steps_total; int nsplit; int steps_per_split; uint32_t smem; };
 
-// MCLIP_BWD_GTMEM=1 hands G to the dX MMA through TMEM (TS form, duplicated layout) instead of shared memory.
-// Numerically identical; measured slower (1.61 vs 1.53 ms at 32768^2 x 512) because of the extra exchange + barriers.
-bool g_in_tmem() {
-  static int cached = -1;
-  if (cached < 0) {
-    const char* e = getenv("MCLIP_BWD_GTMEM");
-    cached = (e && e[0] == '1') ? 1 : 0;
-  }
-  return cached == 1;
-}
-
-// Pairs per cluster.  Default 1: the pair kernel is limited by the ~64 B/clk each SM can ingest from L2, which
-// multicast does not reduce (measured: 1.95 ms with 2 pairs + multicast vs 1.85 ms with 1 pair at 32768^2 x 512,
-// and 4-CTA clusters strand 16 of the 148 SMs).  MCLIP_BWD_PAIRS=2 selects the multicast variant.
-int bwd_cluster_pairs() {
-  static int cached = -1;
-  if (cached < 0) {
-    const char* e = getenv("MCLIP_BWD_PAIRS");
-    cached = (e && e[0] == '2') ? 2 : 1;
-  }
-  return cached;
-}
-
+// (Variants measured and removed in round 2, all numerically identical -- numbers in profiles/r1_ncu_summary.md section 3:
+// 4-CTA clusters with multicast Y tiles 1.95 vs 1.85 ms; G handed over through TMEM 1.61 vs 1.53 ms; transposed pair
+// kernel with a DSMEM exchange 1.98 vs 1.65 ms; single-CTA kernel at D <= 512 4.00 ms.)
 Bwd2Plan plan_bwd2(int64_t M, int64_t N, int64_t D) {
   Bwd2Plan b;
-  b.cpairs = (M > 128) ? bwd_cluster_pairs() : 1;
   b.kch = (int)ceil_div(D, 64);
   b.kpairs = (b.kch + 1) / 2;
   b.ndh = (int)ceil_div(D, 256);
   b.steps_total = (int)ceil_div(N, 256);
-  const int64_t pairs = ceil_div(M, 128 * b.cpairs);       // clusters
-  const int per_wave = b.cpairs == 1 ? 74 : 33;            // clusters resident at once (4-CTA clusters strand 16 SMs)
+  const int64_t pairs = ceil_div(M, 128);                  // clusters
+  const int per_wave = pair_slots();                       // clusters resident at once
   int best = 1;
   double best_cost = 1e30;
   const int max_split = b.steps_total < 32 ? b.steps_total : 32;
@@ -2637,7 +2158,7 @@ Bwd2Plan plan_bwd2(int64_t M, int64_t N, int64_t D) {
 }
 
 // persistent pair kernel: P pairs walk U = row_blocks x steps units
-constexpr int kMaxPairSlots = 74;   // 148 SMs / 2
+constexpr int kMaxPairSlots = 128;  // upper bound used for sizing only; the launch uses pair_slots()
 struct Bwd2PPlan { int kch; int kpairs; int ndh; int steps_total; int64_t units; int npairs; bool cut; uint32_t smem; };
 
 Bwd2PPlan plan_bwd2p(int64_t M, int64_t N, int64_t D, int pair_slots) {
@@ -2676,14 +2197,11 @@ Bwd2PWs bwd2p_ws_layout(int npairs, int64_t N, int64_t D, int64_t n_pad, bool ne
   return w;
 }
 
-// MCLIP_BWD_PERSIST=1 selects the persistent pair kernel.  Measured (B200, bf16, D = 512): 1.50 vs 1.47 ms at
+// Option bwd_persist (MCLIP_BWD_PERSIST=1 at load, or mclip_set_option) selects the persistent pair kernel.  Measured (B200, bf16, D = 512): 1.50 vs 1.47 ms at
 // 32768 x 32768 and 194 vs 198 us at 4096 x 32768 (the W = 8 shape) -- per step both kernels spend the same ~18 % of
 // the issue thread's time waiting for TMA data, and at W = 1 the launch runs into the board power cap either way, so
 // removing the wave quantisation and the CTA prologues buys nothing yet.  Kept opt-in; passes the same parity tests.
-bool use_persistent_bwd() {
-  const char* e = getenv("MCLIP_BWD_PERSIST");   // read per call: tests toggle it
-  return e && e[0] == '1';
-}
+bool use_persistent_bwd() { return options().bwd_persist != 0; }
 
 // workspace carve-up shared by the size query and the launcher
 struct BwdWs { size_t acc, rd, ly2, y16, total; };
@@ -2751,13 +2269,18 @@ int kernel_timing_read(float* total_ms, int* count) {
 }
 
 namespace {
+thread_local int g_timer_suppress = 0;   // > 0 inside a bracket that already covers the launches (mclip_fused_grad)
+struct TimerSuppress {
+  TimerSuppress() { ++g_timer_suppress; }
+  ~TimerSuppress() { --g_timer_suppress; }
+};
 struct ScopedKernelTimer {
   cudaEvent_t a = nullptr, b = nullptr;
   cudaStream_t stream;
   bool active = false;
   explicit ScopedKernelTimer(cudaStream_t s) : stream(s) {
     std::lock_guard<std::mutex> lock(g_timing_mu);
-    if (!g_timing_on) return;
+    if (!g_timing_on || g_timer_suppress > 0) return;
     cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(s, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) return;
     if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
@@ -2776,7 +2299,48 @@ int tc_make_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t D, in
   return make_tmap(map, base, rows, D, ld, dtype, box_rows);
 }
 
+int tc_make_tmap_f32(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, uint32_t box_cols, uint32_t box_rows) {
+  EncodeTiledFn enc;
+  int rc = bind_context();
+  if (rc) return rc;
+  rc = get_encode_fn(&enc);
+  if (rc) return rc;
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
+  const cuuint32_t box[2] = {box_cols, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(f32) failed (%d) rows=%lld cols=%lld ld=%lld", (int)r, (long long)rows, (long long)cols, (long long)ld);
+    return MCLIP_ERR_CUDA;
+  }
+  return MCLIP_OK;
+}
+
 int tc_set_smem(const void* kernel, uint32_t bytes) { return set_smem(kernel, bytes); }
+
+int tc_set_option(const char* name, int value) {
+  if (!name) return MCLIP_ERR_INVALID;
+  Options& o = options();
+  const std::string k(name);
+  if (k == "bwd_persist") o.bwd_persist = value;
+  else if (k == "dbg") o.dbg = kProfile ? value : 0;
+  else if (k == "fused_bwd") o.fused_bwd = value;
+  else { set_error("unknown option '%s'", name); return MCLIP_ERR_INVALID; }
+  return MCLIP_OK;
+}
+int tc_get_option(const char* name, int* value) {
+  if (!name || !value) return MCLIP_ERR_INVALID;
+  const Options& o = options();
+  const std::string k(name);
+  if (k == "bwd_persist") *value = o.bwd_persist;
+  else if (k == "dbg") *value = o.dbg;
+  else if (k == "fused_bwd") *value = o.fused_bwd;
+  else { set_error("unknown option '%s'", name); return MCLIP_ERR_INVALID; }
+  return MCLIP_OK;
+}
 
 bool tc_supported(int64_t M, int64_t N, int64_t D, int64_t ldx, int64_t ldy, int dtype, int op) {
   (void)M; (void)N; (void)op;
@@ -2800,7 +2364,7 @@ size_t tc_block_grad_ws(int64_t M, int64_t N, int64_t D) {
     const size_t v3 = (b.nsplit > 1 ? align_up((size_t)b.nsplit * M * D * sizeof(float), 256) : 0) +
                       align_up(((size_t)2 * m_pad + 2 * (m_pad / 128) + n_pad + 2 * (n_pad / 128) + 64) * sizeof(float), 256) +
                       align_up((size_t)N * D * 2, 256);
-    const size_t vp = bwd2p_ws_layout(kMaxPairSlots, N, D, n_pad, true).total;
+    const size_t vp = bwd2p_ws_layout(pair_slots(), N, D, n_pad, true).total;
     const size_t v23 = v2 > v3 ? v2 : v3;
     return v23 > vp ? v23 : vp;
   }
@@ -2831,10 +2395,7 @@ int tc_row_lse(const RowLseArgs& a) {
   p.diag = a.diag; p.bf16 = a.dtype == MCLIP_DTYPE_BF16;
   p.run_if = a.run_if;
   if (a.run_if && a.diag) { set_error("row_lse(tcgen05): a predicated call cannot write diag"); return MCLIP_ERR_INVALID; }
-  {
-    const char* e = getenv("MCLIP_DBG");
-    p.dbg = e ? atoi(e) : 0;
-  }
+  p.dbg = options().dbg;
   if (a.diag) MCLIP_CUDA_OK(cudaMemsetAsync(a.diag, 0, sizeof(float) * a.M, a.stream));
   dim3 grid((unsigned)ceil_div(a.M, 128), (unsigned)f.nsplit);
   if (pair) {
@@ -2867,97 +2428,6 @@ int tc_row_lse(const RowLseArgs& a) {
   return launch_lse_merge(p.part_m2, p.part_s, p.part_c, f.nsplit, a.M, a.lse, a.rowdot, a.stream, a.run_if);
 }
 
-// transposed CTA-pair backward (D <= 512, no rowdot output)
-int tc_block_grad3(const BlockGradArgs& a) {
-  const Bwd2Plan b = plan_bwd2(a.M, a.N, a.D);
-  const bool bf = a.dtype == MCLIP_DTYPE_BF16;
-  const int64_t n_pad = (int64_t)b.steps_total * 256;
-  const int64_t m_pad = ceil_div(a.M, 128) * 128;
-  // workspace: [acc partials][stats: lx2, bx, xmm, ly2, ymm, mu0][Y16]
-  const size_t acc_bytes = b.nsplit > 1 ? align_up((size_t)b.nsplit * a.M * a.D * sizeof(float), 256) : 0;
-  const size_t stat_floats = (size_t)2 * m_pad + 2 * (m_pad / 128) + n_pad + 2 * (n_pad / 128) + 64;
-  const size_t stat_bytes = align_up(stat_floats * sizeof(float), 256);
-  const size_t y16_bytes = bf ? align_up((size_t)a.N * a.D * 2, 256) : 0;
-  if (acc_bytes + stat_bytes + y16_bytes > a.ws_bytes) { set_error("block_grad(tcgen05): workspace %zu < %zu", a.ws_bytes, acc_bytes + stat_bytes + y16_bytes); return MCLIP_ERR_WORKSPACE; }
-  uint8_t* ws = reinterpret_cast<uint8_t*>(a.ws);
-  float* lx2 = reinterpret_cast<float*>(ws + acc_bytes);
-  float* bx = lx2 + m_pad;
-  float* xmm = bx + m_pad;
-  float* ly2 = xmm + 2 * (m_pad / 128);
-  float* ymm = ly2 + n_pad;
-  float* mu0 = ymm + 2 * (n_pad / 128);
-  const bool has_col = a.w_col != 0.f;
-  prep_bwd3_kernel<<<1, 1024, 0, a.stream>>>(a.lse_x, a.M, m_pad, log2f(a.w_row) + 12.f, has_col ? a.lse_y : nullptr, a.N, n_pad,
-                                             has_col ? log2f(a.w_col) + 12.f : 0.f, lx2, bx, xmm, ly2, ymm, mu0);
-  count_launch();
-  MCLIP_CUDA_OK(cudaGetLastError());
-  const void* y16 = a.Y;
-  int64_t ld16 = a.ldy;
-  if (bf) {
-    __half* dst = reinterpret_cast<__half*>(ws + acc_bytes + stat_bytes);
-    const int64_t n8 = a.N * (a.D / 8);
-    const unsigned blocks = (unsigned)(ceil_div(n8, 256) < 148 * 8 ? ceil_div(n8, 256) : 148 * 8);
-    bf16_to_f16_kernel<<<blocks, 256, 0, a.stream>>>(reinterpret_cast<const __nv_bfloat16*>(a.Y), a.N, a.D, a.ldy, dst);
-    count_launch();
-    MCLIP_CUDA_OK(cudaGetLastError());
-    y16 = dst;
-    ld16 = a.D;
-  }
-  CUtensorMap tmX, tmY, tmY16;
-  int rc = make_tmap(&tmX, a.X, a.M, a.D, a.ldx, a.dtype, 64);
-  if (rc) return rc;
-  rc = make_tmap(&tmY, a.Y, a.N, a.D, a.ldy, a.dtype, 128);
-  if (rc) return rc;
-  rc = make_tmap(&tmY16, y16, a.N, a.D, ld16, MCLIP_DTYPE_F16, 128);
-  if (rc) return rc;
-  Bwd3Params p;
-  p.M = a.M; p.N = a.N; p.D = a.D; p.kpairs = b.kpairs; p.ndh = b.ndh; p.steps_total = b.steps_total;
-  p.steps_per_split = b.steps_per_split; p.nsplit = b.nsplit; p.diag_off = a.diag_off; p.ls = a.logit_scale; p.go = a.grad_out;
-  p.lx2 = lx2; p.bx = bx; p.xmm = xmm; p.ly2 = ly2; p.ymm = ymm; p.mu0 = mu0; p.w_diag = a.w_diag; p.inv_2n = a.inv_2n;
-  p.has_col = has_col ? 1 : 0; p.dX = a.dX; p.lddx = a.lddx; p.acc_ws = reinterpret_cast<float*>(ws);
-  {
-    const char* e = getenv("MCLIP_DBG");
-    p.dbg = e ? atoi(e) : 0;
-  }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(2 * ceil_div(a.M, 128)), (unsigned)b.nsplit);
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = b.smem;
-  cfg.stream = a.stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  if (bf) {
-    rc = set_smem(tc_block_grad3_kernel<true>, b.smem);
-    if (rc) return rc;
-    MCLIP_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_block_grad3_kernel<true>, tmX, tmY, tmY16, p));
-  } else {
-    rc = set_smem(tc_block_grad3_kernel<false>, b.smem);
-    if (rc) return rc;
-    MCLIP_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_block_grad3_kernel<false>, tmX, tmY, tmY16, p));
-  }
-  count_launch();
-  MCLIP_CUDA_OK(cudaGetLastError());
-  if (b.nsplit > 1) {
-    const int64_t n = a.M * a.D;
-    const unsigned blocks = (unsigned)(ceil_div(n, 1024) < 148 * 8 ? ceil_div(n, 1024) : 148 * 8);
-    const float scale = a.inv_2n * (1.f / kGScale);
-    if (bf)
-      acc_to_dx_kernel<__nv_bfloat16><<<blocks, 256, 0, a.stream>>>(p.acc_ws, nullptr, b.nsplit, a.M, a.D, a.logit_scale, a.grad_out,
-                                                                   scale, reinterpret_cast<__nv_bfloat16*>(a.dX), a.lddx, nullptr);
-    else
-      acc_to_dx_kernel<__half><<<blocks, 256, 0, a.stream>>>(p.acc_ws, nullptr, b.nsplit, a.M, a.D, a.logit_scale, a.grad_out, scale,
-                                                            reinterpret_cast<__half*>(a.dX), a.lddx, nullptr);
-    count_launch();
-    MCLIP_CUDA_OK(cudaGetLastError());
-  }
-  return MCLIP_OK;
-}
-
 // CTA-pair backward (D <= 512)
 // pair slots of the current device for this kernel (clusters of 2, 1 CTA per SM), queried once per device
 template <typename K>
@@ -2970,7 +2440,7 @@ int pair_slots_for(K kernel, uint32_t smem, int* out) {
   auto it = cache.find(dev);
   if (it != cache.end()) { *out = it->second; return MCLIP_OK; }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(2 * kMaxPairSlots);
+  cfg.gridDim = dim3(2 * pair_slots());
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem;
   cudaLaunchAttribute attr[1];
@@ -2982,8 +2452,8 @@ int pair_slots_for(K kernel, uint32_t smem, int* out) {
   cfg.numAttrs = 1;
   int n = 0;
   cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kernel, &cfg);
-  if (e != cudaSuccess || n < 1) { (void)cudaGetLastError(); n = kMaxPairSlots; }
-  if (n > kMaxPairSlots) n = kMaxPairSlots;
+  if (e != cudaSuccess || n < 1) { (void)cudaGetLastError(); n = pair_slots(); }
+  if (n > pair_slots()) n = pair_slots();
   cache[dev] = n;
   *out = n;
   return MCLIP_OK;
@@ -2992,7 +2462,7 @@ int pair_slots_for(K kernel, uint32_t smem, int* out) {
 int tc_block_grad2p(const BlockGradArgs& a) {
   const bool bf = a.dtype == MCLIP_DTYPE_BF16;
   int rc;
-  int slots = kMaxPairSlots;
+  int slots = pair_slots();
   {
     const uint32_t smem = kAlignSlack + 8 * kTile8K + 4 * kTile8K + kRing2 * kStage2 + 1536;
     rc = bf ? set_smem(tc_block_grad2p_kernel<true>, smem) : set_smem(tc_block_grad2p_kernel<false>, smem);
@@ -3020,7 +2490,7 @@ int tc_block_grad2p(const BlockGradArgs& a) {
   if (bf) {
     __half* dst = reinterpret_cast<__half*>(ws + w.y16);
     const int64_t n8 = a.N * (a.D / 8);
-    const unsigned blocks = (unsigned)(ceil_div(n8, 256) < 148 * 8 ? ceil_div(n8, 256) : 148 * 8);
+    const unsigned blocks = ew_blocks(n8, 256);
     bf16_to_f16_kernel<<<blocks, 256, 0, a.stream>>>(reinterpret_cast<const __nv_bfloat16*>(a.Y), a.N, a.D, a.ldy, dst);
     count_launch();
     MCLIP_CUDA_OK(cudaGetLastError());
@@ -3041,10 +2511,7 @@ int tc_block_grad2p(const BlockGradArgs& a) {
   p.w_row = a.w_row; p.w_diag = a.w_diag; p.inv_2n = a.inv_2n; p.has_col = has_col ? 1 : 0;
   p.dX = a.dX; p.lddx = a.lddx;
   p.acc_ws = reinterpret_cast<float*>(ws + w.acc); p.rd_ws = reinterpret_cast<float*>(ws + w.rd); p.rowdot = a.rowdot;
-  {
-    const char* e = getenv("MCLIP_DBG");
-    p.dbg = e ? atoi(e) : 0;
-  }
+  p.dbg = options().dbg;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(2 * b.npairs));
   cfg.blockDim = dim3(kThreads);
@@ -3078,6 +2545,106 @@ int tc_block_grad2p(const BlockGradArgs& a) {
   return MCLIP_OK;
 }
 
+namespace {
+// ---- CTA-pair backward (D <= 512): preparation and launch, shared by mclip_block_grad and mclip_fused_grad ----
+struct Bwd2Prep {
+  float* ly2; float* bcol; float* stepmm; float* mu0;   // column statistics (prep_ly2_kernel)
+  const void* y16; int64_t ld16;                        // f16 view / copy of Y
+  bool has_col;
+};
+
+// column statistics of lse_y + the f16 copy of Y (bf16 inputs) into the caller's scratch
+int bwd2_prepare(const BlockGradArgs& a, int64_t n_pad, float* stat_ws, void* y16_ws, Bwd2Prep* out) {
+  Bwd2Prep r;
+  r.ly2 = stat_ws;
+  r.bcol = r.ly2 + n_pad;
+  r.stepmm = r.bcol + n_pad;
+  r.mu0 = r.stepmm + 2 * (n_pad / 256);
+  r.has_col = a.w_col != 0.f;
+  if (r.has_col) {
+    prep_ly2_kernel<<<1, 1024, 0, a.stream>>>(a.lse_y, a.N, n_pad, log2f(a.w_col) + 12.f, r.ly2, r.bcol, r.stepmm, r.mu0);
+    count_launch();
+    MCLIP_CUDA_OK(cudaGetLastError());
+  }
+  r.y16 = a.Y;
+  r.ld16 = a.ldy;
+  if (a.dtype == MCLIP_DTYPE_BF16) {
+    __half* dst = reinterpret_cast<__half*>(y16_ws);
+    const int64_t n8 = a.N * (a.D / 8);
+    bf16_to_f16_kernel<<<ew_blocks(n8, 256), 256, 0, a.stream>>>(reinterpret_cast<const __nv_bfloat16*>(a.Y), a.N, a.D, a.ldy, dst);
+    count_launch();
+    MCLIP_CUDA_OK(cudaGetLastError());
+    r.y16 = dst;
+    r.ld16 = a.D;
+  }
+  *out = r;
+  return MCLIP_OK;
+}
+
+// One launch of tc_block_grad2_kernel over rows [0, a.M) of a.X against all of Y.  `G` (may be null): [a.M, ldg] f16
+// panel that receives every G tile (kStoreG).  With `force_partials` the accumulators always go to acc_ws (f32).
+int bwd2_launch(const BlockGradArgs& a, const Bwd2Plan& b, const Bwd2Prep& pr, float* acc_ws, float* rd_ws, void* G,
+                int64_t ldg, bool force_partials) {
+  const bool bf = a.dtype == MCLIP_DTYPE_BF16;
+  CUtensorMap tmX, tmY, tmY16, tmG;
+  int rc = make_tmap(&tmX, a.X, a.M, a.D, a.ldx, a.dtype, 64);
+  if (rc) return rc;
+  rc = make_tmap(&tmY, a.Y, a.N, a.D, a.ldy, a.dtype, 128);
+  if (rc) return rc;
+  rc = make_tmap(&tmY16, pr.y16, a.N, a.D, pr.ld16, MCLIP_DTYPE_F16, 128);
+  if (rc) return rc;
+  if (G) rc = make_tmap(&tmG, G, a.M, ldg, ldg, MCLIP_DTYPE_F16, 64);
+  else tmG = tmY16;   // unused by the kernel
+  if (rc) return rc;
+  Bwd2Params p;
+  p.M = a.M; p.N = a.N; p.D = a.D; p.kpairs = b.kpairs; p.ndh = b.ndh; p.steps_total = b.steps_total;
+  p.steps_per_split = b.steps_per_split; p.nsplit = force_partials ? 2 : b.nsplit;   // > 1 only selects the partial-store epilogue
+  p.diag_off = a.diag_off; p.ls = a.logit_scale;
+  p.go = a.grad_out; p.lse_x = a.lse_x; p.ly2 = pr.has_col ? pr.ly2 : nullptr; p.bcol = pr.bcol; p.stepmm = pr.stepmm;
+  p.mu0 = pr.mu0; p.w_row = a.w_row; p.w_diag = a.w_diag;
+  p.inv_2n = a.inv_2n; p.has_col = pr.has_col ? 1 : 0; p.dX = a.dX; p.lddx = a.lddx;
+  p.acc_ws = acc_ws; p.rd_ws = rd_ws; p.rowdot = a.rowdot;
+  p.dbg = options().dbg;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * ceil_div(a.M, 128)), (unsigned)b.nsplit);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = b.smem;
+  cfg.stream = a.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+#define MCLIP_LAUNCH_BWD2(BF, SG)                                                                             \
+  do {                                                                                                        \
+    rc = set_smem(tc_block_grad2_kernel<BF, SG>, b.smem);                                                     \
+    if (rc) return rc;                                                                                        \
+    MCLIP_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_block_grad2_kernel<BF, SG>, tmX, tmY, tmY16, tmG, p));          \
+  } while (0)
+  {
+    ScopedKernelTimer timer(a.stream);   // no-op unless bench.py asked for in-situ timing; brackets only this launch
+    if (G) { if (bf) MCLIP_LAUNCH_BWD2(true, true); else MCLIP_LAUNCH_BWD2(false, true); }
+    else { if (bf) MCLIP_LAUNCH_BWD2(true, false); else MCLIP_LAUNCH_BWD2(false, false); }
+  }
+#undef MCLIP_LAUNCH_BWD2
+  count_launch();
+  MCLIP_CUDA_OK(cudaGetLastError());
+  return MCLIP_OK;
+}
+
+template <typename T>
+int launch_acc_to_dx(const float* acc_ws, const float* rd_ws, int nsplit, const BlockGradArgs& a) {
+  const int64_t n = a.M * a.D;
+  acc_to_dx_kernel<T><<<ew_blocks(n, 1024), 256, 0, a.stream>>>(acc_ws, rd_ws, nsplit, a.M, a.D, a.logit_scale, a.grad_out,
+                                                                 a.inv_2n * (1.f / kGScale), reinterpret_cast<T*>(a.dX), a.lddx,
+                                                                 a.rowdot);
+  count_launch();
+  MCLIP_CUDA_OK(cudaGetLastError());
+  return MCLIP_OK;
+}
+
 int tc_block_grad2(const BlockGradArgs& a) {
   const Bwd2Plan b = plan_bwd2(a.M, a.N, a.D);
   const bool bf = a.dtype == MCLIP_DTYPE_BF16;
@@ -3085,107 +2652,219 @@ int tc_block_grad2(const BlockGradArgs& a) {
   const BwdWs w = bwd_ws_layout(b.nsplit, a.M, a.N, a.D, n_pad, bf);
   if (w.total > a.ws_bytes) { set_error("block_grad(tcgen05): workspace %zu < %zu", a.ws_bytes, w.total); return MCLIP_ERR_WORKSPACE; }
   uint8_t* ws = reinterpret_cast<uint8_t*>(a.ws);
-  float* ly2 = reinterpret_cast<float*>(ws + w.ly2);
-  float* bcol = ly2 + n_pad;
-  float* stepmm = bcol + n_pad;
-  float* mu0 = stepmm + 2 * (n_pad / 256);
-  const bool has_col = a.w_col != 0.f;
-  if (has_col) {
-    prep_ly2_kernel<<<1, 1024, 0, a.stream>>>(a.lse_y, a.N, n_pad, log2f(a.w_col) + 12.f, ly2, bcol, stepmm, mu0);
-    count_launch();
-    MCLIP_CUDA_OK(cudaGetLastError());
-  }
-  const void* y16 = a.Y;
-  int64_t ld16 = a.ldy;
-  if (bf) {
-    __half* dst = reinterpret_cast<__half*>(ws + w.y16);
-    const int64_t n8 = a.N * (a.D / 8);
-    const unsigned blocks = (unsigned)(ceil_div(n8, 256) < 148 * 8 ? ceil_div(n8, 256) : 148 * 8);
-    bf16_to_f16_kernel<<<blocks, 256, 0, a.stream>>>(reinterpret_cast<const __nv_bfloat16*>(a.Y), a.N, a.D, a.ldy, dst);
-    count_launch();
-    MCLIP_CUDA_OK(cudaGetLastError());
-    y16 = dst;
-    ld16 = a.D;
-  }
-  CUtensorMap tmX, tmY, tmY16;
-  int rc = make_tmap(&tmX, a.X, a.M, a.D, a.ldx, a.dtype, 64);
+  Bwd2Prep pr;
+  int rc = bwd2_prepare(a, n_pad, reinterpret_cast<float*>(ws + w.ly2), ws + w.y16, &pr);
   if (rc) return rc;
-  rc = make_tmap(&tmY, a.Y, a.N, a.D, a.ldy, a.dtype, 128);
+  float* acc_ws = reinterpret_cast<float*>(ws + w.acc);
+  float* rd_ws = reinterpret_cast<float*>(ws + w.rd);
+  rc = bwd2_launch(a, b, pr, acc_ws, rd_ws, nullptr, 0, false);
   if (rc) return rc;
-  rc = make_tmap(&tmY16, y16, a.N, a.D, ld16, MCLIP_DTYPE_F16, 128);
-  if (rc) return rc;
-  Bwd2Params p;
-  p.M = a.M; p.N = a.N; p.D = a.D; p.kpairs = b.kpairs; p.ndh = b.ndh; p.steps_total = b.steps_total;
-  p.steps_per_split = b.steps_per_split; p.nsplit = b.nsplit; p.diag_off = a.diag_off; p.ls = a.logit_scale;
-  p.go = a.grad_out; p.lse_x = a.lse_x; p.ly2 = has_col ? ly2 : nullptr; p.bcol = bcol; p.stepmm = stepmm; p.mu0 = mu0; p.w_row = a.w_row; p.w_diag = a.w_diag;
-  p.inv_2n = a.inv_2n; p.has_col = has_col ? 1 : 0; p.dX = a.dX; p.lddx = a.lddx;
-  p.acc_ws = reinterpret_cast<float*>(ws + w.acc); p.rd_ws = reinterpret_cast<float*>(ws + w.rd); p.rowdot = a.rowdot;
-  {
-    const char* e = getenv("MCLIP_DBG");
-    p.dbg = e ? atoi(e) : 0;
+  if (b.nsplit > 1) return bf ? launch_acc_to_dx<__nv_bfloat16>(acc_ws, rd_ws, b.nsplit, a) : launch_acc_to_dx<__half>(acc_ws, rd_ws, b.nsplit, a);
+  return MCLIP_OK;
+}
+
+// =================================================================================================
+// shared-recompute backward: ONE recompute of S per logits tile feeds both gradients (4 GEMM units per step, not 5)
+// =================================================================================================
+// For row panels of X (sized so that one launch of the pair kernel fills every SM pair exactly once):
+//   main stream:  tc_block_grad2_kernel<.., kStoreG>   dX[panel] partials + G[panel, :] (f16 * 2^12) -> global scratch
+//                 acc_to_dx_dot_kernel                 dX[panel] (input dtype) and xdot[i] = <X_i, dX_i acc> (for d logit_scale)
+//   side stream:  tc_gemm_tn_kernel                    dY_acc += G[panel, :]^T X16[panel]            (overlaps the next panel)
+// and finally dY = alpha * dY_acc.  Only one [panel x N] strip of G (two buffers) ever exists; the N x N matrix does not.
+// d(logit_scale) comes from Euler's identity: the loss depends on X only through logit_scale * X Y^T, hence
+// sum_i <X_i, dL/dX_i> = logit_scale * dL/d(logit_scale): t = sum_ij G_ij C_ij = sum_i <X_i, (G Y)_i>.
+struct FusedPlan { int64_t panel_rows; int panels; Bwd2Plan b; int64_t n_pad; };
+
+FusedPlan plan_fused(int64_t M, int64_t N, int64_t D) {
+  FusedPlan f;
+  const int slots = pair_slots();
+  const int steps_total = (int)ceil_div(N, 256);
+  // column splits x row blocks per panel: a panel launch should fill the pair slots once; pick the split count that
+  // minimises panels x (steps per CTA + ~3 step-times of per-CTA prologue and accumulator drain)
+  const int64_t rbs = ceil_div(M, 128);
+  int nsplit = 1;
+  double best = 1e30;
+  for (int s = 1; s <= 8 && s <= slots && s <= steps_total; ++s) {
+    const int64_t rb_s = (slots / s) < rbs ? (slots / s) : rbs;
+    const double cost = (double)ceil_div(rbs, rb_s) * ((double)ceil_div(steps_total, s) + 3.0);
+    if (cost < best - 1e-9) { best = cost; nsplit = s; }
   }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(2 * b.cpairs * ceil_div(a.M, 128 * b.cpairs)), (unsigned)b.nsplit);
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = b.smem;
-  cfg.stream = a.stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2 * b.cpairs;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-#define MCLIP_LAUNCH_BWD2(BF, PAIRS, GT)                                                    \
-  do {                                                                                      \
-    rc = set_smem(tc_block_grad2_kernel<BF, PAIRS, GT>, b.smem);                            \
-    if (rc) return rc;                                                                      \
-    MCLIP_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_block_grad2_kernel<BF, PAIRS, GT>, tmX, tmY, tmY16, p)); \
-  } while (0)
-  const bool gt = g_in_tmem();
-  {
-    ScopedKernelTimer timer(a.stream);   // no-op unless bench.py asked for in-situ timing; brackets only this launch
-    if (b.cpairs == 2) {            // multicast variant: shared-memory G only
-      if (bf) MCLIP_LAUNCH_BWD2(true, 2, false); else MCLIP_LAUNCH_BWD2(false, 2, false);
-    } else if (gt) {
-      if (bf) MCLIP_LAUNCH_BWD2(true, 1, true); else MCLIP_LAUNCH_BWD2(false, 1, true);
-    } else {
-      if (bf) MCLIP_LAUNCH_BWD2(true, 1, false); else MCLIP_LAUNCH_BWD2(false, 1, false);
+  int64_t rb = slots / nsplit;                       // row blocks per panel
+  if (rb > rbs) rb = rbs;
+  f.panels = (int)ceil_div(rbs, rb);
+  rb = ceil_div(rbs, f.panels);                      // equalise the panels
+  f.panel_rows = rb * 128;
+  f.b = plan_bwd2(f.panel_rows, N, D);
+  f.b.nsplit = nsplit;
+  f.b.steps_per_split = (int)ceil_div(steps_total, nsplit);
+  f.b.nsplit = (int)ceil_div(steps_total, f.b.steps_per_split);
+  f.n_pad = (int64_t)steps_total * 256;
+  return f;
+}
+
+struct FusedWs { size_t stat, y16, x16, acc_y, acc_x, g, total; };
+FusedWs fused_ws_layout(const FusedPlan& f, int64_t M, int64_t N, int64_t D, bool bf) {
+  FusedWs w;
+  size_t off = 0;
+  w.stat = off;  off += align_up(((size_t)2 * f.n_pad + 2 * (f.n_pad / 256) + 64) * sizeof(float), 256);
+  w.y16 = off;   off += bf ? align_up((size_t)N * D * 2, 256) : 0;
+  w.x16 = off;   off += bf ? align_up((size_t)M * D * 2, 256) : 0;
+  w.acc_y = off; off += align_up((size_t)N * D * sizeof(float), 256);
+  w.acc_x = off; off += align_up((size_t)f.b.nsplit * f.panel_rows * D * sizeof(float), 256);
+  w.g = off;     off += 2 * align_up((size_t)f.panel_rows * f.n_pad * 2, 1024);
+  w.total = off;
+  return w;
+}
+
+// per-device side stream + fork/join events (created once, never destroyed: they live as long as the library)
+struct FusedStreams { cudaStream_t side = nullptr; std::vector<cudaEvent_t> ev; };
+int fused_streams(int nev, FusedStreams** out) {
+  static std::mutex mu;
+  static std::unordered_map<int, FusedStreams> cache;
+  int dev = 0;
+  MCLIP_CUDA_OK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  FusedStreams& fs = cache[dev];
+  if (!fs.side) MCLIP_CUDA_OK(cudaStreamCreateWithFlags(&fs.side, cudaStreamNonBlocking));
+  while ((int)fs.ev.size() < nev) {
+    cudaEvent_t e;
+    MCLIP_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    fs.ev.push_back(e);
+  }
+  *out = &fs;
+  return MCLIP_OK;
+}
+
+// sum of the column-split partials -> dX (input dtype) and xdot[row] = <X[row], sum> / 2^12; one warp per row
+template <typename T>
+__global__ void __launch_bounds__(256)
+acc_to_dx_dot_kernel(const float* __restrict__ acc, int nsplit, int64_t M, int64_t D, const T* __restrict__ X, int64_t ldx,
+                     const float* __restrict__ ls, const float* __restrict__ go, float scale, T* __restrict__ dX, int64_t lddx,
+                     float* __restrict__ xdot) {
+  const float alpha = (go ? go[0] : 1.f) * ls[0] * scale;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t n = M * D;
+  for (int64_t r = warp; r < M; r += nwarps) {
+    float dot = 0.f;
+    for (int64_t d = lane * 4; d < D; d += 128) {     // D % 8 == 0 on this path
+      const int64_t i = r * D + d;
+      float4 a = *reinterpret_cast<const float4*>(acc + i);
+      for (int s = 1; s < nsplit; ++s) {
+        const float4 b = *reinterpret_cast<const float4*>(acc + (int64_t)s * n + i);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      }
+      const T* x = X + r * ldx + d;
+      dot = fmaf(a.x, to_f32<T>(x[0]), dot); dot = fmaf(a.y, to_f32<T>(x[1]), dot);
+      dot = fmaf(a.z, to_f32<T>(x[2]), dot); dot = fmaf(a.w, to_f32<T>(x[3]), dot);
+      T* o = dX + r * lddx + d;
+      o[0] = from_f32<T>(a.x * alpha); o[1] = from_f32<T>(a.y * alpha);
+      o[2] = from_f32<T>(a.z * alpha); o[3] = from_f32<T>(a.w * alpha);
     }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    if (lane == 0) xdot[r] = dot * (1.f / kGScale);
   }
-#undef MCLIP_LAUNCH_BWD2
-  count_launch();
-  MCLIP_CUDA_OK(cudaGetLastError());
-  if (b.nsplit > 1) {
-    const int64_t n = a.M * a.D;
-    const unsigned blocks = (unsigned)(ceil_div(n, 1024) < 148 * 8 ? ceil_div(n, 1024) : 148 * 8);
-    const float scale = a.inv_2n * (1.f / kGScale);
-    if (bf)
-      acc_to_dx_kernel<__nv_bfloat16><<<blocks, 256, 0, a.stream>>>(p.acc_ws, p.rd_ws, b.nsplit, a.M, a.D, a.logit_scale,
-                                                                   a.grad_out, scale,
-                                                                   reinterpret_cast<__nv_bfloat16*>(a.dX), a.lddx, a.rowdot);
-    else
-      acc_to_dx_kernel<__half><<<blocks, 256, 0, a.stream>>>(p.acc_ws, p.rd_ws, b.nsplit, a.M, a.D, a.logit_scale,
-                                                            a.grad_out, scale, reinterpret_cast<__half*>(a.dX), a.lddx,
-                                                            a.rowdot);
+}
+
+template <typename T>
+int fused_grad_impl(const FusedGradArgs& a) {
+  const bool bf = a.dtype == MCLIP_DTYPE_BF16;
+  const FusedPlan f = plan_fused(a.M, a.N, a.D);
+  const FusedWs w = fused_ws_layout(f, a.M, a.N, a.D, bf);
+  if (w.total > a.ws_bytes) { set_error("fused_grad: workspace %zu < %zu", a.ws_bytes, w.total); return MCLIP_ERR_WORKSPACE; }
+  uint8_t* ws = reinterpret_cast<uint8_t*>(a.ws);
+  // bench.py's in-situ bracket covers the whole call here (its two kernels overlap on two streams; the side stream has
+  // been joined back into a.stream when the closing event is recorded); the per-launch brackets inside are suppressed
+  ScopedKernelTimer timer(a.stream);
+  TimerSuppress no_inner;
+  BlockGradArgs g;
+  g.X = a.X; g.Y = a.Y; g.M = a.M; g.N = a.N; g.D = a.D; g.ldx = a.ldx; g.ldy = a.ldy; g.dtype = a.dtype;
+  g.logit_scale = a.logit_scale; g.grad_out = a.grad_out; g.lse_x = a.lse_x; g.lse_y = a.lse_y; g.diag_off = a.diag_off;
+  g.w_row = 1.f; g.w_col = 1.f; g.w_diag = 2.f; g.inv_2n = a.inv_2n; g.dX = a.dX; g.lddx = a.lddx; g.rowdot = nullptr;
+  g.ws = nullptr; g.ws_bytes = 0; g.stream = a.stream;
+  Bwd2Prep pr;
+  int rc = bwd2_prepare(g, f.n_pad, reinterpret_cast<float*>(ws + w.stat), ws + w.y16, &pr);
+  if (rc) return rc;
+  const void* x16 = a.X;
+  int64_t ldx16 = a.ldx;
+  if (bf) {
+    __half* dst = reinterpret_cast<__half*>(ws + w.x16);
+    const int64_t n8 = a.M * (a.D / 8);
+    bf16_to_f16_kernel<<<ew_blocks(n8, 256), 256, 0, a.stream>>>(reinterpret_cast<const __nv_bfloat16*>(a.X), a.M, a.D, a.ldx, dst);
+    count_launch();
+    MCLIP_CUDA_OK(cudaGetLastError());
+    x16 = dst;
+    ldx16 = a.D;
+  }
+  float* acc_y = reinterpret_cast<float*>(ws + w.acc_y);
+  float* acc_x = reinterpret_cast<float*>(ws + w.acc_x);
+  MCLIP_CUDA_OK(cudaMemsetAsync(acc_y, 0, (size_t)a.N * a.D * sizeof(float), a.stream));
+  const size_t g_stride = align_up((size_t)f.panel_rows * f.n_pad * 2, 1024);
+  FusedStreams* fs = nullptr;
+  rc = fused_streams(2 * f.panels + 1, &fs);
+  if (rc) return rc;
+  const int slots = pair_slots();
+  for (int pi = 0; pi < f.panels; ++pi) {
+    const int64_t r0 = (int64_t)pi * f.panel_rows;
+    const int64_t rows = (a.M - r0 < f.panel_rows) ? a.M - r0 : f.panel_rows;
+    void* gbuf = ws + w.g + (size_t)(pi & 1) * g_stride;
+    if (pi >= 2) MCLIP_CUDA_OK(cudaStreamWaitEvent(a.stream, fs->ev[2 * (pi - 2) + 1], 0));   // G buffer free again
+    BlockGradArgs gp = g;
+    gp.X = reinterpret_cast<const T*>(a.X) + r0 * a.ldx;
+    gp.M = rows;
+    gp.lse_x = a.lse_x + r0;
+    gp.diag_off = a.diag_off + r0;
+    gp.dX = reinterpret_cast<T*>(a.dX) + r0 * a.lddx;
+    rc = bwd2_launch(gp, f.b, pr, acc_x, nullptr, gbuf, f.n_pad, true);
+    if (rc) return rc;
+    acc_to_dx_dot_kernel<T><<<ew_blocks(rows * 32, 256), 256, 0, a.stream>>>(
+        acc_x, f.b.nsplit, rows, a.D, reinterpret_cast<const T*>(gp.X), a.ldx, a.logit_scale, a.grad_out,
+        a.inv_2n * (1.f / kGScale), reinterpret_cast<T*>(gp.dX), a.lddx, a.xdot + r0);
+    count_launch();
+    MCLIP_CUDA_OK(cudaGetLastError());
+    MCLIP_CUDA_OK(cudaEventRecord(fs->ev[2 * pi], a.stream));
+    MCLIP_CUDA_OK(cudaStreamWaitEvent(fs->side, fs->ev[2 * pi], 0));
+    rc = launch_gemm_tn(gbuf, f.n_pad, reinterpret_cast<const __half*>(x16) + r0 * ldx16, ldx16, acc_y, a.D, rows, a.N, a.D,
+                        slots, fs->side);
+    if (rc) return rc;
+    MCLIP_CUDA_OK(cudaEventRecord(fs->ev[2 * pi + 1], fs->side));
+  }
+  MCLIP_CUDA_OK(cudaStreamWaitEvent(a.stream, fs->ev[2 * (f.panels - 1) + 1], 0));
+  {
+    const int64_t n = a.N * a.D;
+    acc_to_dx_kernel<T><<<ew_blocks(n, 1024), 256, 0, a.stream>>>(acc_y, nullptr, 1, a.N, a.D, a.logit_scale, a.grad_out,
+                                                                   a.inv_2n * (1.f / kGScale), reinterpret_cast<T*>(a.dY), a.lddy,
+                                                                   nullptr);
     count_launch();
     MCLIP_CUDA_OK(cudaGetLastError());
   }
   return MCLIP_OK;
 }
 
+}  // namespace
+
+bool tc_fused_supported(int64_t M, int64_t N, int64_t D, int64_t ldx, int64_t ldy, int dtype) {
+  if (!options().fused_bwd) return false;
+  if (!tc_supported(M, N, D, ldx, ldy, dtype, MCLIP_OP_BLOCK_GRAD) || D > 512) return false;
+  // pays off once a panel launch is long enough to hide its prologue / drain: >= 16 steps per CTA, >= 2 panels' worth of rows
+  return N >= 8192 && M >= 2048;
+}
+
+size_t tc_fused_grad_ws(int64_t M, int64_t N, int64_t D) {
+  return fused_ws_layout(plan_fused(M, N, D), M, N, D, true).total;
+}
+
+int tc_fused_grad(const FusedGradArgs& a) {
+  if (((uintptr_t)a.X | (uintptr_t)a.Y | (uintptr_t)a.dX | (uintptr_t)a.dY) & 15) { set_error("fused_grad: X/Y/dX/dY must be 16-byte aligned"); return MCLIP_ERR_INVALID; }
+  if (a.D > 512) { set_error("fused_grad: D=%lld > 512", (long long)a.D); return MCLIP_ERR_UNSUPPORTED; }
+  return a.dtype == MCLIP_DTYPE_BF16 ? fused_grad_impl<__nv_bfloat16>(a) : fused_grad_impl<__half>(a);
+}
+
 int tc_block_grad(const BlockGradArgs& a) {
   if (((uintptr_t)a.X | (uintptr_t)a.Y | (uintptr_t)a.dX) & 15) { set_error("block_grad(tcgen05): X/Y/dX must be 16-byte aligned"); return MCLIP_ERR_INVALID; }
   if (!(a.w_row > 0.f) || a.w_col < 0.f) { set_error("block_grad(tcgen05): needs w_row > 0 and w_col >= 0"); return MCLIP_ERR_INVALID; }
-  if (a.D <= 512 && !use_single_cta_bwd()) {
-    // MCLIP_BWD_V3=1 selects the transposed pair kernel (numerically identical, no rowdot output).  It makes both
-    // MMAs math-bound but needs half of G pushed into the peer's shared memory every step; measured 1.98 ms vs
-    // 1.65 ms for the non-transposed kernel at 32768^2 x 512, so the latter stays the default.
-    const char* e = getenv("MCLIP_BWD_V3");
-    const bool v3 = (e && e[0] == '1') && a.rowdot == nullptr;
-    if (v3) return tc_block_grad3(a);
-    return use_persistent_bwd() ? tc_block_grad2p(a) : tc_block_grad2(a);
-  }
+  if (a.D <= 512) return use_persistent_bwd() ? tc_block_grad2p(a) : tc_block_grad2(a);
   const BwdPlan b = plan_bwd(a.M, a.N, a.D);
   if (b.stages < 2) { set_error("block_grad(tcgen05): not enough shared memory for D=%lld", (long long)a.D); return MCLIP_ERR_UNSUPPORTED; }
   const bool bf = a.dtype == MCLIP_DTYPE_BF16;
@@ -3196,7 +2875,7 @@ int tc_block_grad(const BlockGradArgs& a) {
   if (bf) {
     __half* dst = reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(a.ws) + acc_bytes);
     const int64_t n8 = a.N * (a.D / 8);
-    const unsigned blocks = (unsigned)(ceil_div(n8, 256) < 148 * 8 ? ceil_div(n8, 256) : 148 * 8);
+    const unsigned blocks = ew_blocks(n8, 256);
     bf16_to_f16_kernel<<<blocks, 256, 0, a.stream>>>(reinterpret_cast<const __nv_bfloat16*>(a.Y), a.N, a.D, a.ldy, dst);
     count_launch();
     MCLIP_CUDA_OK(cudaGetLastError());
@@ -3236,7 +2915,7 @@ int tc_block_grad(const BlockGradArgs& a) {
   MCLIP_CUDA_OK(cudaGetLastError());
   if (b.nsplit > 1) {
     const int64_t n = a.M * a.D;
-    const unsigned blocks = (unsigned)(ceil_div(n, 1024) < 148 * 8 ? ceil_div(n, 1024) : 148 * 8);
+    const unsigned blocks = ew_blocks(n, 1024);
     const float scale = a.inv_2n * (g_bf16 ? 1.f : 1.f / 4096.f);
     if (bf)
       acc_to_dx_kernel<__nv_bfloat16><<<blocks, 256, 0, a.stream>>>(p.acc_ws, p.rd_ws, b.nsplit, a.M, a.D, a.logit_scale,

@@ -244,6 +244,78 @@ def closed_form(image_all: torch.Tensor, text_all: torch.Tensor, logit_scale: fl
 
 
 # --------------------------------------------------------------------------------------
+# 3b. the same closed forms split into "global statistics once" + "any subset of rows": what the
+#     headline sizes (B = 32768 / 65536) need -- loss and d(logit_scale) are exact over ALL rows and
+#     columns, feature gradients are evaluated on a seeded subset of rows against ALL columns.
+# --------------------------------------------------------------------------------------
+@dataclass
+class GlobalStats:
+    row_lse: torch.Tensor   # [Bg] fp64  LSE_j S_ij
+    col_lse: torch.Tensor   # [Bg] fp64  LSE_i S_ij
+    u: torch.Tensor         # [Bg] fp64  sum_j P^row_ij C_ij   (C = raw dots)
+    v: torch.Tensor         # [Bg] fp64  sum_i P^col_ij C_ij
+    diag: torch.Tensor      # [Bg] fp64  C_ii
+
+
+def global_stats(image_all: torch.Tensor, text_all: torch.Tensor, logit_scale: float, chunk: int = 1024) -> GlobalStats:
+    """Two chunked fp64 passes over S = ls * I T^T (loss.py:102-111 without ever holding [B, B])."""
+    I = image_all.double()
+    T = text_all.double()
+    ls = float(logit_scale)
+    Bg = I.shape[0]
+    out = [torch.empty(Bg, dtype=torch.float64) for _ in range(4)]
+    for k, (A, Bm) in enumerate(((I, T), (T, I))):
+        for s in range(0, Bg, chunk):
+            C = A[s:s + chunk] @ Bm.T
+            S = ls * C
+            lse = torch.logsumexp(S, dim=1)
+            out[2 * k][s:s + chunk] = lse
+            out[2 * k + 1][s:s + chunk] = (torch.exp(S - lse[:, None]) * C).sum(dim=1)
+    return GlobalStats(out[0], out[2], out[1], out[3], (I * T).sum(dim=1))
+
+
+def closed_form_rows(image_all: torch.Tensor, text_all: torch.Tensor, logit_scale: float, world_size: int, rank: int,
+                     local_loss: bool, gather_with_grad: bool, stats: GlobalStats, rows: torch.Tensor,
+                     grad_output: float = 1.0):
+    """Per-rank reference values from precomputed global statistics (same mode table as `closed_form`).
+
+    -> (loss, dI[rows], dT[rows], d_logit_scale); `rows` are LOCAL row indices of the rank's shard.  Loss and
+    d(logit_scale) cover every row / column of the rank (or of the global problem for local_loss=False);
+    the feature gradients are exact for the requested rows (each needs all B_g columns)."""
+    I = image_all.double()
+    T = text_all.double()
+    ls = float(logit_scale)
+    go = float(grad_output)
+    W = world_size
+    Bg = I.shape[0]
+    Bl = Bg // W
+    lo, hi = rank * Bl, (rank + 1) * Bl
+    st = stats
+    per_row = (st.row_lse - ls * st.diag) + (st.col_lse - ls * st.diag)
+    if W == 1 or not local_loss:
+        loss = 0.5 * per_row.mean()
+    else:
+        loss = 0.5 * per_row[lo:hi].mean()
+    own_terms_only = W > 1 and local_loss and not gather_with_grad
+    n_feat = Bg if (W == 1 or (not local_loss and not gather_with_grad)) else Bl
+    g = lo + rows.long()
+    grads = []
+    for A, Bm, lse_x, lse_y in ((I, T, st.row_lse, st.col_lse), (T, I, st.col_lse, st.row_lse)):
+        S = ls * (A[g] @ Bm.T)
+        G = torch.exp(S - lse_x[g, None])
+        if not own_terms_only:
+            G += torch.exp(S - lse_y[None, :])
+        G[torch.arange(g.numel()), g] -= 1.0 if own_terms_only else 2.0
+        grads.append((go * ls / (2.0 * n_feat)) * (G @ Bm))
+    t_all = st.u + st.v - 2.0 * st.diag
+    if W > 1 and local_loss:
+        dls = go * float(t_all[lo:hi].sum()) / (2.0 * Bl)
+    else:
+        dls = go * float(t_all.sum()) / (2.0 * Bg)
+    return loss, grads[0], grads[1], torch.tensor(dls, dtype=torch.float64)
+
+
+# --------------------------------------------------------------------------------------
 # block-level restatements of the two device primitives (used by tests to emulate the C-ABI on
 # CPU for the gloo world_size-2 tests of the host logic, and to check the kernels directly)
 # --------------------------------------------------------------------------------------

@@ -41,11 +41,36 @@ class EmulatedBackend:
 
     def dls_finalize(self, u, v, diag, go, scale):
         self.calls.append("dls_finalize")
-        t = (u.double() + v.double() - 2 * diag.double()).sum()
+        t = u.double().sum()
+        if v is not None:
+            t = t + v.double().sum()
+        if diag is not None:
+            t = t - 2 * diag.double().sum()
         return t.float(), (float(go) * scale * t).float()
 
     def launch_count(self):
         return len(self.calls)
+
+
+class EmulatedFusedBackend(EmulatedBackend):
+    """Adds the oracle statement of mclip_fused_grad (include/mclip_b200.h): both gradients of the full-weight block and
+    xdot[i] = sum_j G_ij <x_i, y_j>, so that the W = 1 shared-recompute branch of the host logic runs on CPU."""
+
+    def fused_supported(self, X, Y):
+        return True
+
+    def fused_grad(self, X, Y, ls, go, lse_x, lse_y, diag_off, inv_2n):
+        self.calls.append("fused_grad")
+        alpha = float(go) * float(ls) * inv_2n
+        Xd, Yd = X.double(), Y.double()
+        C = Xd @ Yd.T
+        S = float(ls) * C
+        G = torch.exp(S - lse_x.double()[:, None]) + torch.exp(S - lse_y.double()[None, :])
+        i = torch.arange(X.shape[0])
+        j = i + diag_off
+        ok = (j >= 0) & (j < Y.shape[0])
+        G[i[ok], j[ok]] -= 2.0
+        return (alpha * (G @ Yd)).to(X.dtype), (alpha * (G.T @ Xd)).to(X.dtype), (G * C).sum(dim=1).float()
 
 
 LOG2E = 1.4426950408889634

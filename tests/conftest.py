@@ -3,6 +3,10 @@ import sys
 
 import pytest
 
+# tests (and only tests) may install an oracle-backed stand-in for the C-ABI primitives to run the multi-rank host logic
+# under gloo on CPU: mamba_clip_b200._cabi.set_backend_override refuses without this opt-in
+os.environ.setdefault("MCLIP_ALLOW_TEST_BACKEND", "1")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

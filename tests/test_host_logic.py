@@ -248,3 +248,91 @@ def test_gloo_ranks_against_golden(k):
         assert abs(dls - gd) <= 3e-5 * abs(gd) + 1.2e-7 * case["go"] * max(1.0, case["ls"])
         assert float((torch.from_numpy(di).double() - gi).norm()) <= 2e-5 * float(gi.norm()) + floor
         assert float((torch.from_numpy(dt).double() - gt).norm()) <= 2e-5 * float(gt.norm()) + floor
+
+
+@pytest.mark.parametrize("k", [0, 3, 7, 12, 20])
+def test_single_process_fused_backward_branch_against_reference_golden(k):
+    """W = 1 with a backend that offers mclip_fused_grad: both feature gradients from one call, d(logit_scale) through
+    Euler's identity (sum of xdot) -- must still reproduce the reference's golden outputs."""
+    from mamba_clip_b200 import ClipLoss, _cabi
+    from tests._emul import EmulatedFusedBackend
+    case = SINGLE_CASES[k % len(SINGLE_CASES)]
+    kk = k % len(SINGLE_CASES)
+    be = EmulatedFusedBackend()
+    _cabi.set_backend_override(be)
+    try:
+        img, txt = O.make_features(case["B"], case["D"], seed=case["seed"], correlated=case["corr"])
+        if case["bf16"]:
+            img, txt = img.bfloat16().float(), txt.bfloat16().float()
+        a = img.clone().requires_grad_(True)
+        b = txt.clone().requires_grad_(True)
+        ls = torch.tensor(case["ls"], requires_grad=True)
+        loss = ClipLoss()(a, b, ls)["contrastive_loss"]
+        loss.backward(torch.tensor(case["go"]))
+    finally:
+        _cabi.set_backend_override(None)
+    assert "fused_grad" in be.calls and "block_grad" not in be.calls
+    gl, gd = float(SINGLE[f"c{kk}_loss"]), float(SINGLE[f"c{kk}_dls"])
+    assert abs(float(loss) - gl) <= 3e-6 * max(1.0, abs(gl)) + 2e-7
+    assert abs(float(ls.grad) - gd) <= 3e-5 * abs(gd) + 4e-7 * case["go"] * max(1.0, case["ls"])
+    floor = grad_floor(case["go"], case["ls"], case["B"])
+    for key, g in (("di", a.grad), ("dt", b.grad)):
+        if f"c{kk}_{key}_full" in SINGLE:
+            ref = torch.from_numpy(SINGLE[f"c{kk}_{key}_full"]).double()
+            assert float((g.double() - ref).norm()) <= 2e-5 * float(ref.norm()) + floor
+
+
+def test_double_backward_raises_instead_of_returning_zeros(emulated):
+    from mamba_clip_b200 import ClipLoss
+    img, txt = O.make_features(8, 16, seed=2)
+    a = img.clone().requires_grad_(True)
+    loss = ClipLoss()(a, txt, torch.tensor(5.0), output_dict=False)
+    (g,) = torch.autograd.grad(loss, a, create_graph=True)
+    with pytest.raises(RuntimeError, match="once_differentiable|twice|does not require grad"):
+        g.sum().backward()
+
+
+def test_backend_override_is_refused_without_the_test_opt_in(monkeypatch):
+    from mamba_clip_b200 import _cabi
+    monkeypatch.delenv("MCLIP_ALLOW_TEST_BACKEND", raising=False)
+    with pytest.raises(RuntimeError, match="test hook"):
+        _cabi.set_backend_override(object())
+    _cabi.set_backend_override(None)
+
+
+def _mismatch_worker(rank, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=2)
+    try:
+        from mamba_clip_b200 import ClipLoss, _cabi
+        from tests._emul import EmulatedBackend
+        _cabi.set_backend_override(EmulatedBackend())
+        a = torch.randn(8 if rank == 0 else 12, 16)          # the ranks disagree on B_l
+        try:
+            ClipLoss(True, True, True, rank, 2)(a, a, torch.tensor(10.0))
+            q.put((rank, "no error"))
+        except ValueError as e:
+            q.put((rank, str(e)))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_unequal_shards_raise_on_every_rank():
+    """SURVEY 8(b) "Errors": equal B_l across ranks is validated before anything is launched (the reference would hang
+    or fail inside torch); one tiny all-reduce the first time a (group, shape, dtype) is seen."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    procs = [ctx.Process(target=_mismatch_worker, args=(r, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all("same shape" in m for m in res.values()), res

@@ -114,3 +114,44 @@ def test_block_primitives_compose_to_closed_form():
         diag = (img[lo:hi].double() * txt[lo:hi].double()).sum(1)
         dls = go / (2 * Bl) * float((u + v - 2 * diag).sum())
         assert abs(dls - float(cf.d_logit_scale)) < 1e-12 * max(1.0, abs(dls))
+
+
+@pytest.mark.parametrize("W", [1, 2, 4])
+@pytest.mark.parametrize("local_loss,gwg", [(False, False), (False, True), (True, False), (True, True)])
+def test_subset_closed_form_matches_full_closed_form(W, local_loss, gwg):
+    """global_stats + closed_form_rows (the checker bench.py and the C3/C4-size GPU tests use: loss and d(logit_scale)
+    over everything, feature gradients on a row subset) against the full closed form and the rank emulation."""
+    Bl, D, ls, go = 24, 40, 17.0, 2.5
+    img, txt = O.make_features(W * Bl, D, seed=31 + W, correlated=True)
+    st = O.global_stats(img, txt, ls, chunk=7)
+    port = O.ref_port_ranks(img, txt, ls, W, local_loss, gwg, grad_output=go)
+    rows = torch.tensor([0, 5, 6, 23, 11])
+    for r in range(W):
+        loss, di, dt, dls = O.closed_form_rows(img, txt, ls, W, r, local_loss, gwg, st, rows, grad_output=go)
+        cf = O.closed_form(img, txt, ls, W, r, local_loss, gwg, grad_output=go, chunk=9)
+        assert abs(float(loss) - float(cf.loss)) <= 1e-12 * max(1.0, abs(float(cf.loss)))
+        assert abs(float(dls) - float(cf.d_logit_scale)) <= 1e-11 * max(1.0, abs(float(cf.d_logit_scale)))
+        assert O.rel_err(di, cf.d_image[rows]) <= 1e-9 and O.rel_err(dt, cf.d_text[rows]) <= 1e-9   # fp64, cancelling terms
+        assert abs(float(loss) - float(port[r].loss)) <= 3e-6 * max(1.0, abs(float(port[r].loss)))
+        # the fp32 port only resolves these saturated-softmax gradients to ~1e-6 of their natural scale (see check_grad)
+        floor = 1e-6 * go * ls / (2 * Bl) * rows.numel() ** 0.5
+        for got, want in ((di, port[r].d_image[rows]), (dt, port[r].d_text[rows])):
+            assert float((got - want.double()).norm()) <= 2e-5 * float(want.norm()) + floor
+
+
+def test_reference_copy_matches_port_when_present():
+    """oracle/_ref (the byte-for-byte copy of the reference's loss.py made by oracle/build_ref.py, present in the build
+    container and shipped to the GPU box) gives what the port gives; skipped where the copy does not exist."""
+    from oracle import build_ref
+    if not build_ref.available():
+        pytest.skip("oracle/_ref not built (reference tree absent)")
+    ref = build_ref.load()
+    img, txt = O.make_features(96, 64, seed=5, correlated=True)
+    a = img.clone().requires_grad_(True)
+    b = txt.clone().requires_grad_(True)
+    s = torch.tensor(14.2857, requires_grad=True)
+    loss = ref.ClipLoss(cache_labels=True)(a, b, s)["contrastive_loss"]
+    loss.backward(torch.tensor(3.0))
+    port = O.ref_port_single(img, txt, 14.2857, grad_output=3.0)
+    assert torch.equal(loss.detach(), port.loss)
+    assert torch.equal(a.grad, port.d_image) and torch.equal(b.grad, port.d_text) and torch.equal(s.grad, port.d_logit_scale)
