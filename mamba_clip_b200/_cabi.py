@@ -13,7 +13,8 @@ from typing import Optional, Tuple
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmclip_b200.so")
+# MCLIP_LIB_PATH: development only (e.g. a -DMCLIP_PROFILE build next to the release library)
+LIB_PATH = os.environ.get("MCLIP_LIB_PATH") or os.path.join(_HERE, "libmclip_b200.so")
 
 ABI_VERSION = 4
 DTYPE_CODES = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}

@@ -36,10 +36,16 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
+PROFILE_LIB = os.path.join(HERE, "libmclip_b200_prof.so")
+
+
 def build(force: bool = False, verbose: bool = False, profile: bool = False) -> str:
-    if not force and not is_stale():
+    """Release library (default) or, with `profile`, a separate -DMCLIP_PROFILE library next to it (in-kernel cycle
+    accounting, selected at run time with MCLIP_LIB_PATH=.../libmclip_b200_prof.so MCLIP_DBG=16)."""
+    out = PROFILE_LIB if profile else LIB
+    if not force and not profile and not is_stale():
         return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES]]
+    cmd = [_nvcc(), *NVCC_FLAGS, "-o", out, *[os.path.join(CSRC, s) for s in SOURCES]]
     if profile:
         cmd.insert(1, "-DMCLIP_PROFILE")
     if verbose:
@@ -50,7 +56,7 @@ def build(force: bool = False, verbose: bool = False, profile: bool = False) -> 
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
     if verbose:
         sys.stderr.write(res.stderr)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

@@ -85,6 +85,11 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, uint32_t
   asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c_inner), "r"(c_outer) : "memory");
 }
+// 3-D variants for tile-major scratch ([tile][64 rows][64 elements]: one box = one contiguous 8 KB block of global memory)
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src, int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
@@ -236,6 +241,13 @@ __device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const CUtensorMap*
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(c_inner), "r"(c_outer), "r"(bar & kPeerBitMask)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_cg2(uint32_t dst, const CUtensorMap* m, int32_t c0, int32_t c1, int32_t c2,
+                                                uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2), "r"(bar & kPeerBitMask)
       : "memory");
 }
 // Same, multicast: the box lands at `dst` in every CTA of `mask` and each copy credits its own pair leader.

@@ -863,6 +863,8 @@ struct Bwd2Params {
   float* rd_ws;
   float* rowdot;
   int dbg;              // development switches (MCLIP_DBG): 1 = epilogue without math, 2 = no S MMAs, 4 = no dX MMAs, 8 = always two exps
+  int g_tiles_per_row;  // kStoreG: 64-column tiles per 64-row block of the tile-major G scratch (= n_pad / 64)
+  void* g_ptr;          // kStoreG: the scratch, [row blocks of 64][g_tiles_per_row][64 x 64 f16 in SWIZZLE_128B byte order]
 };
 
 constexpr uint32_t kTile8K = 64 * 64 * 2;     // [64 rows x 64 k]
@@ -934,15 +936,13 @@ __device__ __forceinline__ void bwd2_chunk_fast(const uint32_t (&v)[32], uint32_
   }
 }
 
-// kStoreG: every G tile (f16 * 2^12, exactly what the dX MMA consumes) is also written to global memory with TMA
-// stores straight out of the shared-memory operand buffer (warp 3; the buffer is released by the dX commit AND the
-// store's read completion).  The panel-wise shared-recompute backward (tc_fused_grad) feeds dY = G^T X from it, so
+// kStoreG: every G tile (f16 * 2^12, exactly what the dX MMA consumes) is also copied to global memory straight out of
+// the shared-memory operand buffer (warps 2 and 3; the buffer is released by the dX commit AND the copies' reads).  The panel-wise shared-recompute backward (tc_fused_grad) feeds dY = G^T X from it, so
 // that one S recompute serves both gradients.
 template <bool kBF16, bool kStoreG>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
-                      const __grid_constant__ CUtensorMap tmY16, const __grid_constant__ CUtensorMap tmG,
-                      const Bwd2Params p) {
+                      const __grid_constant__ CUtensorMap tmY16, const Bwd2Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = align1024(smem_u32(smem_raw));
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -985,12 +985,11 @@ tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmY);
     tma_prefetch_desc(&tmY16);
-    if (kStoreG) tma_prefetch_desc(&tmG);
     for (int s = 0; s < kRing2; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
     mbar_init(xfull_bar, 2);
     for (int b = 0; b < 2; ++b) { mbar_init(sfull_bar(b), 1); mbar_init(sread_bar(b), 2 * (kEpiThreads / 32)); }
     mbar_init(gfull_bar, 2 * (kEpiThreads / 32));
-    mbar_init(gempty_bar, kStoreG ? 2 : 1);
+    mbar_init(gempty_bar, kStoreG ? 3 : 1);     // dX commit (+ the two G-store warps)
     mbar_init(gstore_bar, kEpiThreads / 32);
     mbar_init(dxfull_bar, 1);
     fence_barrier_init();
@@ -1144,20 +1143,37 @@ tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                (int)blockIdx.x, nsteps, clock64() - t_begin, t_full, t_gfull, (clock64() - t_begin) / max(nsteps, 1),
                t_full / max(nsteps, 1), t_gfull / max(nsteps, 1));
     }
-  } else if (kStoreG && warp == 3) {
-    if (lane == 0) {
-      // ---------------- G store (both CTAs): shared-memory operand tiles -> global G panel ----------------
-      for (int st = 0; st < nsteps; ++st) {
-        mbar_wait(gstore_bar, st & 1);            // this CTA's 8 epilogue warps wrote G(st) and fenced it for the async proxy
-        const int32_t n0 = (s0 + st) * 256;
-#pragma unroll
-        for (int kc = 0; kc < 4; ++kc) tma_store_2d(&tmG, g_base + kc * kTile8K, n0 + 64 * kc, (int32_t)m0);
-        tma_store_commit();
-        tma_store_wait_read0();                   // the tiles have been read out of shared memory
-        mbar_arrive(gempty_bar);
+  } else if (kStoreG && (warp == 2 || warp == 3)) {
+    // ---------------- G store (both CTAs, two warps): shared-memory operand tiles -> global tile-major scratch ----------------
+    // Plain coalesced ld.shared / st.global copies, NOT TMA stores: the TMA unit of an SM is the resource this kernel is
+    // bound by (64 B/clk of operand loads); 32 KB of TMA stores per step queued behind those loads cost ~1300 clk/step
+    // (measured, profiles/r2_summary.md).  The four [64 x 64] f16 tiles of a step are contiguous both in shared memory
+    // and in the scratch (tile-major), and are copied byte for byte, i.e. in their SWIZZLE_128B order: the consumer
+    // (tc_gemm_tn_kernel) loads them back with an unswizzled TMA box and uses the same descriptors.
+    const int sw = warp - 2;
+    const bool sprof = kProfile && (p.dbg & 16) != 0 && lane == 0;
+    long long s_wait = 0, s_copy = 0, s_begin = clock64();
+    for (int st = 0; st < nsteps; ++st) {
+      long long t0 = sprof ? clock64() : 0;
+      mbar_wait(gstore_bar, st & 1);            // this CTA's 8 epilogue warps wrote G(st)
+      if (sprof) { s_wait += clock64() - t0; t0 = clock64(); }
+      uint8_t* gdst = reinterpret_cast<uint8_t*>(p.g_ptr) +
+                      (((size_t)(m0 >> 6) * p.g_tiles_per_row + (size_t)(s0 + st) * 4) << 13) + lane * 16;
+      const uint32_t gsrc = g_base + lane * 16;
+#pragma unroll 8
+      for (int i = sw; i < 64; i += 2) {
+        uint32_t a, b, c, d;
+        ld_shared_v4(gsrc + i * 512, a, b, c, d);
+        asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(gdst + i * 512), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
       }
-      tma_store_wait_all0();
+      if (sprof) s_copy += clock64() - t0;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(gempty_bar);   // the tiles have been read out of shared memory
     }
+    if (sprof && sw == 1 && blockIdx.x < 4 && blockIdx.y == 0)
+      printf("[gst cta %d] total=%lld clk  wait_gstore=%lld  copy=%lld (per step: total %lld gstore %lld copy %lld)\n",
+             (int)blockIdx.x, clock64() - s_begin, s_wait, s_copy, (clock64() - s_begin) / max(nsteps, 1), s_wait / max(nsteps, 1),
+             s_copy / max(nsteps, 1));
   } else if (warp >= kEpiWarp0) {
     // ---------------- epilogue: S -> G (f16 * 2^12) into shared memory; finally dX out ----------------
     const int ew = warp - kEpiWarp0;
@@ -1869,7 +1885,8 @@ bwd2p_fixup_kernel(const float* __restrict__ acc_ws, const float* __restrict__ r
   }
 }
 
-// Column statistics for the backward kernel (one block of 1024 threads):
+// Column statistics for the backward kernel.  Every block first reduces the global (min, max) of ly2 itself (N floats
+// from L2 -- cheaper than a second launch or a grid-wide barrier), then handles its share of the 256-column steps:
 //   ly2[j]  = lse_y[j] * log2e - lw_col              (+inf in the padding up to a multiple of 256)
 //   mu0     = midpoint of the ly2 range;  bcol[j] = 2^(mu0 - ly2[j])  (0 in the padding)
 //   stepmm  = (min, max) of ly2 over each 256-column step
@@ -1899,12 +1916,12 @@ prep_ly2_kernel(const float* __restrict__ lse_y, int64_t N, int64_t n_pad, float
       mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     }
-    if (lane == 0) { mu_s = 0.5f * mn + 0.5f * mx; mu0_out[0] = mu_s; }
+    if (lane == 0) { mu_s = 0.5f * mn + 0.5f * mx; if (blockIdx.x == 0) mu0_out[0] = mu_s; }
   }
   __syncthreads();
   const float mu = mu_s;
   const int64_t nsteps = n_pad / 256;
-  for (int64_t st = warp; st < nsteps; st += 32) {
+  for (int64_t st = (int64_t)blockIdx.x * 32 + warp; st < nsteps; st += (int64_t)gridDim.x * 32) {
     float smn = INFINITY, smx = -INFINITY;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -1983,6 +2000,10 @@ int sm_count() {
   return n;
 }
 int pair_slots() { return sm_count() / 2; }
+unsigned prep_blocks(int64_t n_pad) {   // prep_ly2_kernel: one warp per 256-column step, ~8 of its 32 warps busy per block
+  const int64_t want = ceil_div(n_pad / 256, 8);
+  return (unsigned)(want < 1 ? 1 : (want > 64 ? 64 : want));
+}
 unsigned ew_blocks(int64_t work_items, int per_block) {   // grid of an elementwise helper: at most 8 blocks per SM
   const int64_t want = ceil_div(work_items, per_block), cap = (int64_t)sm_count() * 8;
   return (unsigned)(want < cap ? want : cap);
@@ -2319,6 +2340,26 @@ int tc_make_tmap_f32(CUtensorMap* map, const void* base, int64_t rows, int64_t c
   return MCLIP_OK;
 }
 
+int tc_make_tmap_tiles(CUtensorMap* map, const void* base, int64_t ntiles) {
+  EncodeTiledFn enc;
+  int rc = bind_context();
+  if (rc) return rc;
+  rc = get_encode_fn(&enc);
+  if (rc) return rc;
+  const cuuint64_t gdim[3] = {64, 64, (cuuint64_t)ntiles};
+  const cuuint64_t gstride[2] = {128, 8192};
+  const cuuint32_t box[3] = {64, 64, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(tiles) failed (%d) ntiles=%lld", (int)r, (long long)ntiles);
+    return MCLIP_ERR_CUDA;
+  }
+  return MCLIP_OK;
+}
+
 int tc_set_smem(const void* kernel, uint32_t bytes) { return set_smem(kernel, bytes); }
 
 int tc_set_option(const char* name, int value) {
@@ -2481,7 +2522,7 @@ int tc_block_grad2p(const BlockGradArgs& a) {
   float* mu0 = stepmm + 2 * (n_pad / 256);
   const bool has_col = a.w_col != 0.f;
   if (has_col) {
-    prep_ly2_kernel<<<1, 1024, 0, a.stream>>>(a.lse_y, a.N, n_pad, log2f(a.w_col) + 12.f, ly2, bcol, stepmm, mu0);
+    prep_ly2_kernel<<<prep_blocks(n_pad), 1024, 0, a.stream>>>(a.lse_y, a.N, n_pad, log2f(a.w_col) + 12.f, ly2, bcol, stepmm, mu0);
     count_launch();
     MCLIP_CUDA_OK(cudaGetLastError());
   }
@@ -2562,7 +2603,7 @@ int bwd2_prepare(const BlockGradArgs& a, int64_t n_pad, float* stat_ws, void* y1
   r.mu0 = r.stepmm + 2 * (n_pad / 256);
   r.has_col = a.w_col != 0.f;
   if (r.has_col) {
-    prep_ly2_kernel<<<1, 1024, 0, a.stream>>>(a.lse_y, a.N, n_pad, log2f(a.w_col) + 12.f, r.ly2, r.bcol, r.stepmm, r.mu0);
+    prep_ly2_kernel<<<prep_blocks(n_pad), 1024, 0, a.stream>>>(a.lse_y, a.N, n_pad, log2f(a.w_col) + 12.f, r.ly2, r.bcol, r.stepmm, r.mu0);
     count_launch();
     MCLIP_CUDA_OK(cudaGetLastError());
   }
@@ -2581,20 +2622,18 @@ int bwd2_prepare(const BlockGradArgs& a, int64_t n_pad, float* stat_ws, void* y1
   return MCLIP_OK;
 }
 
-// One launch of tc_block_grad2_kernel over rows [0, a.M) of a.X against all of Y.  `G` (may be null): [a.M, ldg] f16
-// panel that receives every G tile (kStoreG).  With `force_partials` the accumulators always go to acc_ws (f32).
+// One launch of tc_block_grad2_kernel over rows [0, a.M) of a.X against all of Y.  `G` (may be null): tile-major f16
+// scratch [ceil(a.M / 128) * 2][n_pad / 64][64][64] that receives every G tile (kStoreG).  With `force_partials` the
+// accumulators always go to acc_ws (f32).
 int bwd2_launch(const BlockGradArgs& a, const Bwd2Plan& b, const Bwd2Prep& pr, float* acc_ws, float* rd_ws, void* G,
-                int64_t ldg, bool force_partials) {
+                int64_t n_pad, bool force_partials) {
   const bool bf = a.dtype == MCLIP_DTYPE_BF16;
-  CUtensorMap tmX, tmY, tmY16, tmG;
+  CUtensorMap tmX, tmY, tmY16;
   int rc = make_tmap(&tmX, a.X, a.M, a.D, a.ldx, a.dtype, 64);
   if (rc) return rc;
   rc = make_tmap(&tmY, a.Y, a.N, a.D, a.ldy, a.dtype, 128);
   if (rc) return rc;
   rc = make_tmap(&tmY16, pr.y16, a.N, a.D, pr.ld16, MCLIP_DTYPE_F16, 128);
-  if (rc) return rc;
-  if (G) rc = make_tmap(&tmG, G, a.M, ldg, ldg, MCLIP_DTYPE_F16, 64);
-  else tmG = tmY16;   // unused by the kernel
   if (rc) return rc;
   Bwd2Params p;
   p.M = a.M; p.N = a.N; p.D = a.D; p.kpairs = b.kpairs; p.ndh = b.ndh; p.steps_total = b.steps_total;
@@ -2605,6 +2644,8 @@ int bwd2_launch(const BlockGradArgs& a, const Bwd2Plan& b, const Bwd2Prep& pr, f
   p.inv_2n = a.inv_2n; p.has_col = pr.has_col ? 1 : 0; p.dX = a.dX; p.lddx = a.lddx;
   p.acc_ws = acc_ws; p.rd_ws = rd_ws; p.rowdot = a.rowdot;
   p.dbg = options().dbg;
+  p.g_tiles_per_row = (int)(n_pad / 64);
+  p.g_ptr = G;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(2 * ceil_div(a.M, 128)), (unsigned)b.nsplit);
   cfg.blockDim = dim3(kThreads);
@@ -2621,7 +2662,7 @@ int bwd2_launch(const BlockGradArgs& a, const Bwd2Plan& b, const Bwd2Prep& pr, f
   do {                                                                                                        \
     rc = set_smem(tc_block_grad2_kernel<BF, SG>, b.smem);                                                     \
     if (rc) return rc;                                                                                        \
-    MCLIP_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_block_grad2_kernel<BF, SG>, tmX, tmY, tmY16, tmG, p));          \
+    MCLIP_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_block_grad2_kernel<BF, SG>, tmX, tmY, tmY16, p));               \
   } while (0)
   {
     ScopedKernelTimer timer(a.stream);   // no-op unless bench.py asked for in-situ timing; brackets only this launch
@@ -2799,7 +2840,6 @@ int fused_grad_impl(const FusedGradArgs& a) {
   }
   float* acc_y = reinterpret_cast<float*>(ws + w.acc_y);
   float* acc_x = reinterpret_cast<float*>(ws + w.acc_x);
-  MCLIP_CUDA_OK(cudaMemsetAsync(acc_y, 0, (size_t)a.N * a.D * sizeof(float), a.stream));
   const size_t g_stride = align_up((size_t)f.panel_rows * f.n_pad * 2, 1024);
   FusedStreams* fs = nullptr;
   rc = fused_streams(2 * f.panels + 1, &fs);
@@ -2825,8 +2865,8 @@ int fused_grad_impl(const FusedGradArgs& a) {
     MCLIP_CUDA_OK(cudaGetLastError());
     MCLIP_CUDA_OK(cudaEventRecord(fs->ev[2 * pi], a.stream));
     MCLIP_CUDA_OK(cudaStreamWaitEvent(fs->side, fs->ev[2 * pi], 0));
-    rc = launch_gemm_tn(gbuf, f.n_pad, reinterpret_cast<const __half*>(x16) + r0 * ldx16, ldx16, acc_y, a.D, rows, a.N, a.D,
-                        slots, fs->side);
+    rc = launch_gemm_tn(gbuf, f.n_pad / 64, reinterpret_cast<const __half*>(x16) + r0 * ldx16, ldx16, acc_y, a.D, rows, a.N, a.D,
+                        slots, options().dbg, pi == 0, fs->side);
     if (rc) return rc;
     MCLIP_CUDA_OK(cudaEventRecord(fs->ev[2 * pi + 1], fs->side));
   }
