@@ -939,17 +939,24 @@ __device__ __forceinline__ void bwd2_chunk_fast(const uint32_t (&v)[32], uint32_
 // kStoreG: every G tile (f16 * 2^12, exactly what the dX MMA consumes) is also copied to global memory straight out of
 // the shared-memory operand buffer (warps 2 and 3; the buffer is released by the dX commit AND the copies' reads).  The panel-wise shared-recompute backward (tc_fused_grad) feeds dY = G^T X from it, so
 // that one S recompute serves both gradients.
-template <bool kBF16, bool kStoreG>
+// kNX = 8: D <= 512 -- X block = 8 tiles (64 KB), ring of 4 stages, TMEM = 2 S buffers (2 x 128 columns) + dX (256): the S
+//          MMAs run two steps ahead of the dX MMAs.
+// kNX = 12: 512 < D <= 768 -- X block = 12 tiles (96 KB), ring of 3 stages, TMEM = 1 S buffer (128) + dX (384): S runs one
+//          step ahead; S(st+1) is issued as soon as the epilogue has pulled S(st) out of TMEM (`sread`), behind dX(st-1)
+//          in the tensor pipe, so the single buffer costs no bubble.  Same per-flop operand traffic as D = 512.
+template <bool kBF16, bool kStoreG, int kNX>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
                       const __grid_constant__ CUtensorMap tmY16, const Bwd2Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = align1024(smem_u32(smem_raw));
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t x_base = smem_base;                              // [8][64 rows][64 k]   64 KB
-  const uint32_t g_base = x_base + 8 * kTile8K;                   // [4][64 rows][64 y]    32 KB (single buffer)
-  const uint32_t ring_base = g_base + 4 * kTile8K;                // [kRing2][2][128][64]  128 KB
-  const uint32_t misc_base = ring_base + kRing2 * kStage2;
+  constexpr bool kBig = kNX > 8;
+  constexpr int kRing = kBig ? 3 : kRing2;
+  const uint32_t x_base = smem_base;                              // [kNX][64 rows][64 k]  64 / 96 KB
+  const uint32_t g_base = x_base + kNX * kTile8K;                 // [4][64 rows][64 y]    32 KB (single buffer)
+  const uint32_t ring_base = g_base + 4 * kTile8K;                // [kRing][2][128][64]   128 / 96 KB
+  const uint32_t misc_base = ring_base + kRing * kStage2;
   uint8_t* misc_gen = smem_gen + (misc_base - smem_base);
   const uint32_t bar_base = misc_base;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };             // leader: both CTAs' TMA bytes
@@ -979,13 +986,16 @@ tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   const int s1 = min(p.steps_total, s0 + p.steps_per_split);
   const int nsteps = s1 - s0;
   constexpr uint32_t kTmemCols = 512;
-  constexpr uint32_t kDxCol = 256;
+  constexpr uint32_t kDxCol = kBig ? 128 : 256;
+  // S buffer / barrier slot and mbarrier phase of step st
+  auto sbuf = [](int st) { return kBig ? 0 : (st & 1); };
+  auto sphase = [](int st) { return (uint32_t)(kBig ? (st & 1) : ((st >> 1) & 1)); };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmY);
     tma_prefetch_desc(&tmY16);
-    for (int s = 0; s < kRing2; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < kRing; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
     mbar_init(xfull_bar, 2);
     for (int b = 0; b < 2; ++b) { mbar_init(sfull_bar(b), 1); mbar_init(sread_bar(b), 2 * (kEpiThreads / 32)); }
     mbar_init(gfull_bar, 2 * (kEpiThreads / 32));
@@ -1005,14 +1015,14 @@ tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   if (warp == 0) {
     if (lane == 0) {
       // ---------------- TMA producer (both CTAs; bytes are credited to the leader's barriers) ----------------
-      if (leader) mbar_expect_tx(xfull_bar, 2 * 8 * kTile8K); else mbar_arrive_cluster(xfull_bar, leader_rank);
-      for (int c = 0; c < 8; ++c) tma_load_2d_cg2(x_base + c * kTile8K, &tmX, c * 64, (int32_t)m0, xfull_bar);
+      if (leader) mbar_expect_tx(xfull_bar, 2 * kNX * kTile8K); else mbar_arrive_cluster(xfull_bar, leader_rank);
+      for (int c = 0; c < kNX; ++c) tma_load_2d_cg2(x_base + c * kTile8K, &tmX, c * 64, (int32_t)m0, xfull_bar);
       uint32_t it = 0;
       const bool pprof = kProfile && (p.dbg & 16) != 0;
       long long p_empty = 0, p_begin = clock64();
       auto stage_begin = [&]() -> uint32_t {
-        const int s = it % kRing2;
-        const uint32_t ph = (it / kRing2) & 1;
+        const int s = it % kRing;
+        const uint32_t ph = (it / kRing) & 1;
         const long long t0 = pprof ? clock64() : 0;
         mbar_wait(empty_bar(s), ph ^ 1);
         if (pprof) p_empty += clock64() - t0;
@@ -1045,10 +1055,10 @@ tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
           }
         }
       };
-      if (nsteps > 0) load_s(0);
-      if (nsteps > 1) load_s(1);
+      constexpr int kAhead = kBig ? 1 : 2;       // how many steps S runs ahead of dX
+      for (int st = 0; st < kAhead && st < nsteps; ++st) load_s(st);
       for (int st = 0; st < nsteps; ++st) {
-        if (st + 2 < nsteps) load_s(st + 2);
+        if (st + kAhead < nsteps) load_s(st + kAhead);
         load_dx(st);
       }
       if (pprof && blockIdx.x < 4 && blockIdx.y == 0)
@@ -1066,8 +1076,8 @@ tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       const bool prof = kProfile && (p.dbg & 16) != 0 && elected;
       long long t_full = 0, t_gfull = 0, t_begin = clock64();
       auto stage_wait = [&]() -> uint32_t {
-        const int s = it % kRing2;
-        const uint32_t ph = (it / kRing2) & 1;
+        const int s = it % kRing;
+        const uint32_t ph = (it / kRing) & 1;
         const long long t0 = prof ? clock64() : 0;
         mbar_wait(full_bar(s), ph);
         if (prof) t_full += clock64() - t0;
@@ -1076,7 +1086,7 @@ tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         return (uint32_t)s;
       };
       auto issue_s = [&](int st) {
-        const int buf = st & 1;
+        const int buf = sbuf(st);
         // S buffer `buf` was last read by the epilogue of step st-2, whose gfull arrival the dX issue of that step
         // has already waited for; nothing more to wait on here.
         const uint32_t d_tmem = tmem_base + buf * 128;
@@ -1128,13 +1138,13 @@ tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
           }
         }
       };
-      if (nsteps > 0) issue_s(0);
-      if (nsteps > 1) issue_s(1);
+      constexpr int kAhead = kBig ? 1 : 2;
+      for (int st = 0; st < kAhead && st < nsteps; ++st) issue_s(st);
       for (int st = 0; st < nsteps; ++st) {
-        if (st + 2 < nsteps) {
-          mbar_wait(sread_bar(st & 1), (st >> 1) & 1);   // S(st) is in registers: its TMEM buffer may be overwritten
+        if (st + kAhead < nsteps) {
+          mbar_wait(sread_bar(sbuf(st)), sphase(st));   // S(st) is in registers: its TMEM buffer may be overwritten
           tc_fence_after();
-          issue_s(st + 2);
+          issue_s(st + kAhead);
         }
         issue_dx(st);
       }
@@ -1218,8 +1228,8 @@ tc_block_grad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     const bool eprof = kProfile && (p.dbg & 16) != 0 && warp == kEpiWarp0 && lane == 0;
     long long e_sfull = 0, e_gempty = 0, e_begin = clock64();
     for (int st = 0; st < nsteps; ++st) {
-      const int buf = st & 1;
-      const uint32_t bph = (st >> 1) & 1;
+      const int buf = sbuf(st);
+      const uint32_t bph = sphase(st);
       const int64_t n0 = (int64_t)(s0 + st) * 256;
       {
         const long long t0 = eprof ? clock64() : 0;
@@ -1973,11 +1983,13 @@ struct Options {
   int bwd_persist;   // MCLIP_BWD_PERSIST: persistent CTA-pair backward kernel (stream-K vehicle)
   int dbg;           // MCLIP_DBG: development masks; only honoured by -DMCLIP_PROFILE builds
   int fused_bwd;     // MCLIP_FUSED_BWD: shared-recompute backward (one S recompute for dX and dY) where it applies
+  int bwd768_pair;   // MCLIP_BWD768_PAIR: CTA-pair backward kernel for 512 < D <= 768 (0: single-CTA kernel, one S recompute per 256-wide slice of D)
   Options() {
     auto geti = [](const char* k, int dflt) { const char* e = getenv(k); return e ? atoi(e) : dflt; };
     bwd_persist = geti("MCLIP_BWD_PERSIST", 0);
     dbg = kProfile ? geti("MCLIP_DBG", 0) : 0;
     fused_bwd = geti("MCLIP_FUSED_BWD", 1);
+    bwd768_pair = geti("MCLIP_BWD768_PAIR", 1);
   }
 };
 Options& options() {
@@ -2174,7 +2186,8 @@ Bwd2Plan plan_bwd2(int64_t M, int64_t N, int64_t D) {
   }
   b.nsplit = best;
   b.steps_per_split = (int)ceil_div(b.steps_total, best);
-  b.smem = kAlignSlack + 8 * kTile8K + 4 * kTile8K + kRing2 * kStage2 + 1536;
+  b.smem = D <= 512 ? kAlignSlack + 8 * kTile8K + 4 * kTile8K + kRing2 * kStage2 + 1536     // 64 KB X + 32 KB G + 4 x 32 KB ring
+                    : kAlignSlack + 12 * kTile8K + 4 * kTile8K + 3 * kStage2 + 1536;        // 96 KB X + 32 KB G + 3 x 32 KB ring
   return b;
 }
 
@@ -2369,6 +2382,7 @@ int tc_set_option(const char* name, int value) {
   if (k == "bwd_persist") o.bwd_persist = value;
   else if (k == "dbg") o.dbg = kProfile ? value : 0;
   else if (k == "fused_bwd") o.fused_bwd = value;
+  else if (k == "bwd768_pair") o.bwd768_pair = value;
   else { set_error("unknown option '%s'", name); return MCLIP_ERR_INVALID; }
   return MCLIP_OK;
 }
@@ -2379,6 +2393,7 @@ int tc_get_option(const char* name, int* value) {
   if (k == "bwd_persist") *value = o.bwd_persist;
   else if (k == "dbg") *value = o.dbg;
   else if (k == "fused_bwd") *value = o.fused_bwd;
+  else if (k == "bwd768_pair") *value = o.bwd768_pair;
   else { set_error("unknown option '%s'", name); return MCLIP_ERR_INVALID; }
   return MCLIP_OK;
 }
@@ -2410,7 +2425,10 @@ size_t tc_block_grad_ws(int64_t M, int64_t N, int64_t D) {
     return v23 > vp ? v23 : vp;
   }
   const BwdPlan b = plan_bwd(M, N, D);
-  return (b.nsplit > 1 ? align_up((size_t)b.nsplit * M * (D + 1) * sizeof(float), 256) : 0) + align_up((size_t)N * D * 2, 256);
+  const size_t v1 = (b.nsplit > 1 ? align_up((size_t)b.nsplit * M * (D + 1) * sizeof(float), 256) : 0) + align_up((size_t)N * D * 2, 256);
+  const Bwd2Plan b2 = plan_bwd2(M, N, D);
+  const size_t v2 = bwd_ws_layout(b2.nsplit, M, N, D, (int64_t)b2.steps_total * 256, true).total;
+  return v1 > v2 ? v1 : v2;
 }
 
 int tc_row_lse(const RowLseArgs& a) {
@@ -2658,16 +2676,19 @@ int bwd2_launch(const BlockGradArgs& a, const Bwd2Plan& b, const Bwd2Prep& pr, f
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-#define MCLIP_LAUNCH_BWD2(BF, SG)                                                                             \
+#define MCLIP_LAUNCH_BWD2(BF, SG, NX)                                                                         \
   do {                                                                                                        \
-    rc = set_smem(tc_block_grad2_kernel<BF, SG>, b.smem);                                                     \
+    rc = set_smem(tc_block_grad2_kernel<BF, SG, NX>, b.smem);                                                 \
     if (rc) return rc;                                                                                        \
-    MCLIP_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_block_grad2_kernel<BF, SG>, tmX, tmY, tmY16, p));               \
+    MCLIP_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_block_grad2_kernel<BF, SG, NX>, tmX, tmY, tmY16, p));           \
   } while (0)
   {
     ScopedKernelTimer timer(a.stream);   // no-op unless bench.py asked for in-situ timing; brackets only this launch
-    if (G) { if (bf) MCLIP_LAUNCH_BWD2(true, true); else MCLIP_LAUNCH_BWD2(false, true); }
-    else { if (bf) MCLIP_LAUNCH_BWD2(true, false); else MCLIP_LAUNCH_BWD2(false, false); }
+    if (a.D > 512) {                     // 512 < D <= 768: 12 X tiles, one S buffer (no G store: the dY GEMM stops at D = 512)
+      if (G) { set_error("block_grad(tcgen05): the G store needs D <= 512"); return MCLIP_ERR_UNSUPPORTED; }
+      if (bf) MCLIP_LAUNCH_BWD2(true, false, 12); else MCLIP_LAUNCH_BWD2(false, false, 12);
+    } else if (G) { if (bf) MCLIP_LAUNCH_BWD2(true, true, 8); else MCLIP_LAUNCH_BWD2(false, true, 8); }
+    else { if (bf) MCLIP_LAUNCH_BWD2(true, false, 8); else MCLIP_LAUNCH_BWD2(false, false, 8); }
   }
 #undef MCLIP_LAUNCH_BWD2
   count_launch();
@@ -2905,6 +2926,7 @@ int tc_block_grad(const BlockGradArgs& a) {
   if (((uintptr_t)a.X | (uintptr_t)a.Y | (uintptr_t)a.dX) & 15) { set_error("block_grad(tcgen05): X/Y/dX must be 16-byte aligned"); return MCLIP_ERR_INVALID; }
   if (!(a.w_row > 0.f) || a.w_col < 0.f) { set_error("block_grad(tcgen05): needs w_row > 0 and w_col >= 0"); return MCLIP_ERR_INVALID; }
   if (a.D <= 512) return use_persistent_bwd() ? tc_block_grad2p(a) : tc_block_grad2(a);
+  if (options().bwd768_pair) return tc_block_grad2(a);    // 512 < D <= 768: CTA-pair kernel with one S buffer
   const BwdPlan b = plan_bwd(a.M, a.N, a.D);
   if (b.stages < 2) { set_error("block_grad(tcgen05): not enough shared memory for D=%lld", (long long)a.D); return MCLIP_ERR_UNSUPPORTED; }
   const bool bf = a.dtype == MCLIP_DTYPE_BF16;

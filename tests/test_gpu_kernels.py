@@ -115,6 +115,11 @@ GRAD_CASES = [
     (TC, torch.bfloat16, 512, 4096, 512, 100.0, 1024, (1, 1, 2)),
     (TC, torch.bfloat16, 256, 3000, 384, 14.2857, 0, (1, 0, 1)),
     (TC, torch.bfloat16, 2048, 2048, 512, 14.2857, 0, (1, 1, 2)),
+    # 512 < D <= 768: CTA-pair kernel with 12 X tiles and ONE S buffer (S one step ahead of dX)
+    (TC, torch.bfloat16, 384, 2048, 768, 20.0, 0, (1, 1, 2)),
+    (TC, torch.bfloat16, 200, 700, 640, 14.2857, 100, (1, 1, 2)),
+    (TC, torch.bfloat16, 130, 300, 520, 30.0, 0, (1, 0, 1)),
+    (TC, torch.bfloat16, 1024, 4096, 768, 100.0, 512, (1, 1, 2)),
 ]
 
 
@@ -145,27 +150,6 @@ def test_block_grad(path, dtype, M, N, D, ls, diag_off, w, want_rowdot):
     # rowdot = sum_j P_ij c_ij: P inherits the fp32 rounding of s = ls * c (|s| up to ls), i.e. ~eps * ls relative
     rd_tol = (4 * 1.2e-7 * max(1.0, abs(ls)) + 1e-6) if dtype == torch.float32 else 2e-3
     assert float((rd.cpu().double() - ref_rd).abs().max()) <= rd_tol * max(1.0, float(ref_rd.abs().max()))
-
-
-@pytest.mark.parametrize("M,N,D,ls,diag_off,w", [(128, 256, 512, 14.2857, 0, (1, 1, 2)), (300, 1000, 384, 30.0, 17, (1, 1, 2)),
-                                                 (512, 4096, 512, 100.0, 1024, (1, 0, 1)), (2048, 2048, 512, 14.2857, 0, (1, 1, 2))])
-def test_block_grad_transposed_pair_kernel(M, N, D, ls, diag_off, w, monkeypatch):
-    """MCLIP_BWD_V3=1: the transposed CTA-pair kernel (G exchanged through the peer's shared memory) gives the
-    same dX as the oracle."""
-    monkeypatch.setenv("MCLIP_BWD_V3", "1")
-    be = backend(TC)
-    x, y = feats(M, N, D, torch.bfloat16, seed=M * 3 + N, correlated=True)
-    xf, yf = x.float(), y.float()
-    lse_x, _ = O.block_row_lse(xf, yf, ls, None)
-    lse_y, _ = O.block_row_lse(yf, xf, ls, None)
-    ref_dx, _ = O.block_grad(xf, yf, ls, lse_x, lse_y, diag_off, *w, alpha=3.0 * ls / (2 * M))
-    dx, rd = be.block_grad(x.cuda(), y.cuda(), torch.tensor([ls], device="cuda"), torch.tensor([3.0], device="cuda"),
-                           lse_x.float().cuda(), lse_y.float().cuda() if w[1] else None, diag_off,
-                           float(w[0]), float(w[1]), float(w[2]), 1.0 / (2 * M), False)
-    torch.cuda.synchronize()
-    scale = 3.0 * ls / (2 * M) * M ** 0.5
-    assert rd is None
-    assert float((dx.cpu().double() - ref_dx).norm()) <= 2e-3 * float(ref_dx.norm()) + 8 * 1.2e-7 * max(1.0, ls) * scale
 
 
 PAIR_CASES = [
@@ -284,12 +268,12 @@ def test_pair_forward_matches_one_sided_forward_in_the_loss():
 @pytest.mark.parametrize("M,N,D,ls,diag_off,w", [(128, 256, 512, 14.2857, 0, (1, 1, 2)), (300, 1000, 384, 30.0, 17, (1, 1, 2)),
                                                  (640, 768, 512, 20.0, 0, (1, 1, 2)), (512, 4096, 512, 100.0, 1024, (1, 0, 1)),
                                                  (4096, 4096, 512, 14.2857, 0, (1, 1, 2))])
-def test_block_grad_persistent_pair_kernel(M, N, D, ls, diag_off, w, monkeypatch):
-    """MCLIP_BWD_PERSIST=1: the persistent CTA-pair kernel (pairs walk ranges of (row block, step) units, row blocks cut
+def test_block_grad_persistent_pair_kernel(M, N, D, ls, diag_off, w, persistent_backward):
+    """Option bwd_persist = 1: the persistent CTA-pair kernel (pairs walk ranges of (row block, step) units, row blocks cut
     by a range boundary go through f32 partials + fix-up) gives the same dX and rowdot as the oracle.  (640, 768) and
     (4096, 4096) make pairs cross row-block boundaries."""
-    monkeypatch.setenv("MCLIP_BWD_PERSIST", "1")
     be = backend(TC)
+    assert be.get_option("bwd_persist") == 1
     x, y = feats(M, N, D, torch.bfloat16, seed=M * 3 + N, correlated=True)
     xf, yf = x.float(), y.float()
     lse_x, _ = O.block_row_lse(xf, yf, ls, None)
@@ -302,6 +286,15 @@ def test_block_grad_persistent_pair_kernel(M, N, D, ls, diag_off, w, monkeypatch
     scale = 3.0 * ls / (2 * M) * M ** 0.5
     assert float((dx.cpu().double() - ref_dx).norm()) <= 2e-3 * float(ref_dx.norm()) + 8 * 1.2e-7 * max(1.0, ls) * scale
     assert float((rd.cpu().double() - ref_rd).abs().max()) <= 2e-3 * max(1.0, float(ref_rd.abs().max()))
+
+
+@pytest.fixture()
+def persistent_backward():
+    """Switch the library option for the duration of a test (the environment is only read when the library loads)."""
+    be = backend(TC)
+    be.set_option("bwd_persist", 1)
+    yield
+    be.set_option("bwd_persist", 0)
 
 
 def load_single():
