@@ -332,10 +332,16 @@ class CudaBackend:
         _check(self.lib, rc, "mclip_loss_finalize")
         return out
 
-    def normalize_rows(self, x, out_dtype, eps):
+    def normalize_rows(self, x, out_dtype, eps, out=None):
+        """`out` (optional): a [M, D] row-major view to write into -- e.g. the rank's own slot of an all-gather buffer."""
         dev = self._prep(x)
         M, D = x.shape
-        y = torch.empty((M, D), dtype=out_dtype, device=dev)
+        if out is None:
+            y = torch.empty((M, D), dtype=out_dtype, device=dev)
+        else:
+            if out.shape != (M, D) or out.dtype != out_dtype or out.stride(1) != 1 or out.device != dev:
+                raise ValueError("normalize_rows: `out` must be a [M, D] row-major tensor of the output dtype on the same device")
+            y = out
         with self._DeviceGuard(dev):
             rc = self.lib.mclip_normalize_rows(_ptr(x), M, D, x.stride(0), float(eps), DTYPE_CODES[out_dtype], _ptr(y),
                                                y.stride(0), None, ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))

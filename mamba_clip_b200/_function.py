@@ -80,19 +80,48 @@ class _Done:
         return None
 
 
+_comm_streams = {}
+
+
+class _EventWait:
+    """Work handle of a collective issued on the per-device communication stream: `wait()` makes the current stream wait
+    for the event recorded right behind it."""
+
+    def __init__(self, event):
+        self.event = event
+
+    def wait(self):
+        torch.cuda.current_stream().wait_event(self.event)
+
+
+def _on_comm_stream(dev, fn):
+    """Run `fn()` (direct NCCL calls) on the device's communication stream, ordered after everything already queued on the
+    current stream; returns a handle whose `wait()` makes the current stream wait for it.  EVERY direct NCCL call of the
+    loss goes through here: one communicator, one stream, program order -- collectives never run concurrently with each
+    other, only next to the compute kernels."""
+    cs = _comm_streams.get(dev.index)
+    if cs is None:
+        cs = _comm_streams[dev.index] = torch.cuda.Stream(device=dev)
+    cs.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(cs):
+        fn()
+        ev = torch.cuda.Event()
+        ev.record(cs)
+    return _EventWait(ev)
+
+
 def _gather_into(out, x, group, comm=None):
     """All-gather into a caller-provided buffer: directly through NCCL on the current stream when a direct
     communicator exists (see _nccl.py), else through torch.distributed.  Returns a handle with `.wait()`."""
     if comm is not None:
-        comm.all_gather(out, x)
-        return _Done
+        return _on_comm_stream(x.device, lambda: comm.all_gather(out, x))
     try:
         return dist.all_gather_into_tensor(out, x, group=group, async_op=True)
     except (RuntimeError, NotImplementedError):  # backends without the flat variant
         return dist.all_gather(list(out.chunk(dist.get_world_size(group), dim=0)), x, group=group, async_op=True)
 
 
-def _forward_impl(be, xi, xt, ls, local_loss, gather_with_grad, rank, W, group, need_ls, run=_EAGER):
+def _forward_impl(be, xi, xt, ls, local_loss, gather_with_grad, rank, W, group, need_ls, run=_EAGER, gathered=None):
     """Everything `ClipLoss.forward` launches, on already-cast contiguous inputs.  Returns the state dict that
     `_backward_impl` consumes.  Kernel launches are grouped into segments (`run.seg`) separated by the collectives:
     a segment is pure stream work without host synchronisation, so the graph runner can capture and replay it, while
@@ -101,17 +130,23 @@ def _forward_impl(be, xi, xt, ls, local_loss, gather_with_grad, rank, W, group, 
     dev = xi.device
     comm = _nccl.direct_comm(group, dev) if (W > 1 and dev.type == "cuda") else None
     if W > 1:
-        all_t = run.buffer("all_t", (W * Bl, D), xt.dtype, dev)
-        all_i = run.buffer("all_i", (W * Bl, D), xi.dtype, dev)
+        if gathered is not None:
+            # the producer epilogue already wrote this rank's shards into its slots of the gather buffers (xi / xt are
+            # views of them): the all-gathers run in place, no staging copy of the shard
+            all_i, all_t = gathered
+        else:
+            all_t = run.buffer("all_t", (W * Bl, D), xt.dtype, dev)
+            all_i = run.buffer("all_i", (W * Bl, D), xi.dtype, dev)
         if comm is not None:
-            # ONE communicator, ONE stream: both feature gathers go out as a single grouped NCCL launch on the compute
-            # stream (never two collectives of different communicators in flight on one device)
-            comm.all_gather_many(((all_t, xt), (all_i, xi)))
-            work_t = work_i = _Done
+            # ONE communicator, ONE communication stream, program order: the text gather, then the image gather.  The
+            # forward kernels only wait for the first; the second runs next to them (never two collectives at once)
+            work_t = _on_comm_stream(dev, lambda: comm.all_gather(all_t, xt))
+            work_i = _on_comm_stream(dev, lambda: comm.all_gather(all_i, xi))
         else:
             # c10d: both gathers in flight on its own stream; the image gather overlaps the first kernels
-            work_t = _gather_into(all_t, xt, group, None)
-            work_i = _gather_into(all_i, xi, group, None)
+            # (a c10d all-gather must not alias its input with a slot of its output: copy the pre-placed shards out)
+            work_t = _gather_into(all_t, xt.clone() if gathered is not None else xt, group, None)
+            work_i = _gather_into(all_i, xi.clone() if gathered is not None else xi, group, None)
         off = int(rank) * Bl
         work_t.wait()
     else:
@@ -473,6 +508,64 @@ class ClipLossFunction(torch.autograd.Function):
         if d_txt is not None:
             d_txt = d_txt.to(ctx.in_dtypes[1])
         return d_img, d_txt, d_ls, None, None, None, None, None
+
+
+class ClipLossFromProjectionsFunction(torch.autograd.Function):
+    """Producer epilogue fused into the gather prologue (reference model.py:1011-1017,1051 +
+    loss.py:16-44): raw fp32 tower projections -> ONE kernel per tower that L2-normalises each row, rounds it to the
+    16-bit compute dtype and writes it straight into this rank's slot of the all-gather buffer -> in-place NCCL all-gather
+    -> the fused loss.  Backward: the loss kernels' feature gradients go through the normalisation backward kernel and
+    come out as fp32 gradients of the raw projections.  Same values as `ClipLoss(normalize_features(a), normalize_features(b), ls)`."""
+
+    @staticmethod
+    def forward(ctx, image_proj, text_proj, logit_scale, dtype, eps, local_loss, gather_with_grad, rank, world_size, group):
+        be = _cabi.get_backend()
+        dev = image_proj.device
+        pi = image_proj.detach().to(torch.float32).contiguous()
+        pt = text_proj.detach().to(torch.float32).contiguous()
+        Bl, D = pi.shape
+        W = int(world_size)
+        off = int(rank) * Bl if W > 1 else 0
+        all_i = torch.empty((W * Bl, D), dtype=dtype, device=dev)
+        all_t = torch.empty((W * Bl, D), dtype=dtype, device=dev)
+        xi = be.normalize_rows(pi, dtype, eps, out=all_i[off:off + Bl])
+        xt = be.normalize_rows(pt, dtype, eps, out=all_t[off:off + Bl])
+        if torch.is_tensor(logit_scale):
+            ls = logit_scale.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
+        else:
+            ls = torch.full((1,), float(logit_scale), dtype=torch.float32, device=dev)
+        need_ls = torch.is_tensor(logit_scale) and logit_scale.requires_grad
+        st = _forward_impl(be, xi, xt, ls, bool(local_loss), bool(gather_with_grad), int(rank), W, group, need_ls,
+                           gathered=(all_i, all_t) if W > 1 else None)
+        loss = st.pop("loss")
+        ctx.save_for_backward(pi, pt, *(st.pop(k) for k in _SAVED_KEYS))
+        ctx.state = st
+        ctx.eps = eps
+        ctx.cfg = (bool(local_loss), bool(gather_with_grad), W, group)
+        ctx.in_dtypes = (image_proj.dtype, text_proj.dtype)
+        ctx.ls_meta = (logit_scale.dtype, logit_scale.shape, logit_scale.device) if torch.is_tensor(logit_scale) else None
+        return loss
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_out):
+        be = _cabi.get_backend()
+        local_loss, gather_with_grad, W, group = ctx.cfg
+        need_i, need_t, need_ls = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        need_ls = need_ls and ctx.ls_meta is not None
+        pi, pt, *saved = ctx.saved_tensors
+        st = dict(ctx.state)
+        st.update(zip(_SAVED_KEYS, saved))
+        go = grad_out.detach().to(device=pi.device, dtype=torch.float32).reshape(1).contiguous()
+        d_img, d_txt, d_ls = _backward_impl(be, st, go, local_loss, gather_with_grad, W, group, need_i, need_t, need_ls)
+        if d_img is not None:
+            d_img = be.normalize_rows_bwd(pi, d_img.contiguous(), ctx.eps).to(ctx.in_dtypes[0])
+        if d_txt is not None:
+            d_txt = be.normalize_rows_bwd(pt, d_txt.contiguous(), ctx.eps).to(ctx.in_dtypes[1])
+        if d_ls is not None:
+            dt, shape, dev = ctx.ls_meta
+            d_ls = d_ls.reshape(shape).to(device=dev, dtype=dt)
+        return (d_img, d_txt, d_ls) + (None,) * 7
 
 
 class ClipLossChunkFunction(torch.autograd.Function):

@@ -67,9 +67,17 @@ def _worker(rank, W, port, jobs, q):
             b = txt[rank * Bl:(rank + 1) * Bl].to(dev).requires_grad_(True)
             ls = torch.tensor(job["ls"], device=dev, requires_grad=True)
             crit = ClipLoss(job["local_loss"], job["gwg"], True, rank, W)
+            if job.get("proj"):
+                # raw projections -> fused normalise + cast into the gather slot -> in-place all-gather -> loss
+                from mamba_clip_b200.producer import clip_loss_from_projections
+                a = (a.detach().float() * 3.0).requires_grad_(True)
+                b = (b.detach().float() * 0.5).requires_grad_(True)
             for _ in range(reps):
                 a.grad = b.grad = ls.grad = None
-                loss = crit(a, b, ls)["contrastive_loss"]
+                if job.get("proj"):
+                    loss = clip_loss_from_projections(crit, a, b, ls, dtype=torch.bfloat16)["contrastive_loss"]
+                else:
+                    loss = crit(a, b, ls)["contrastive_loss"]
                 loss.backward(torch.tensor(job["go"], device=dev))
             q.put((j, rank, float(loss.detach()), a.grad.float().cpu().numpy(), b.grad.float().cpu().numpy(), float(ls.grad)))
         mamba_clip_b200.enable_cuda_graphs(False)
@@ -215,3 +223,31 @@ def test_unequal_shards_raise_on_every_rank():
         p.join(timeout=120)
         assert p.exitcode == 0
     assert all("same shape" in m for m in res.values()), res
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
+def test_nccl_two_ranks_loss_from_projections_in_place_gather():
+    """Producer epilogue fused into the gather prologue at W = 2: scaled (un-normalised) fp32 projections in, loss and the
+    projections' gradients out, against the oracle's rank emulation run through F.normalize in fp64."""
+    W, Bl, D, ls, go = 2, 300, 256, 20.0, 2.0
+    jobs = [dict(Bl=Bl, D=D, dtype="float32", seed=55, corr=True, ls=ls, go=go, local_loss=ll, gwg=gw, proj=True)
+            for ll, gw in ((True, True), (False, False))]
+    out = _run(W, jobs)
+    import torch.nn.functional as F
+    for j, job in enumerate(jobs):
+        img, txt = _features(W, job)
+        # the worker scales its shard by 3.0 / 0.5 before normalising: normalisation undoes it, the gradient sees 1/scale
+        ref = O.ref_port_ranks(F.normalize(img * 3.0, dim=-1).bfloat16().float(), F.normalize(txt * 0.5, dim=-1).bfloat16().float(),
+                               ls, W, job["local_loss"], job["gwg"], grad_output=go)
+        for r in range(W):
+            loss, di, dt, dls = out[(j, r)]
+            assert abs(loss - float(ref[r].loss)) <= 2e-3 * abs(float(ref[r].loss)) + 1e-6
+            assert abs(dls - float(ref[r].d_logit_scale)) <= 2e-3 * abs(float(ref[r].d_logit_scale)) + 1e-7
+            # gradients w.r.t. the raw projections are tangential: check orthogonality to the projection rows and the norm
+            # ratio against the feature-gradient of the reference pushed through the fp64 normalisation backward
+            for got, want, scale, feats in ((di, ref[r].d_image, 3.0, img), (dt, ref[r].d_text, 0.5, txt)):
+                x = (feats[r * Bl:(r + 1) * Bl].double() * scale).requires_grad_(True)
+                F.normalize(x, dim=-1).backward(want.double())
+                amp = float(want.double().norm()) / max(float((x.grad * float(x.detach().norm(dim=1).mean())).norm()), 1e-30)
+                err = float((torch.from_numpy(got).double() - x.grad).norm())
+                assert err <= 2e-3 * max(1.0, amp) * float(x.grad.norm()) + 1e-9, (job, r, err / float(x.grad.norm()), amp)
