@@ -23,11 +23,11 @@
 extern "C" {
 #endif
 
-#define MCLIP_ABI_VERSION 4
+#define MCLIP_ABI_VERSION 5
 
 enum { MCLIP_DTYPE_F32 = 0, MCLIP_DTYPE_BF16 = 1, MCLIP_DTYPE_F16 = 2 };
 enum { MCLIP_PATH_AUTO = 0, MCLIP_PATH_SIMT = 1, MCLIP_PATH_TCGEN05 = 2 };
-enum { MCLIP_OP_ROW_LSE = 0, MCLIP_OP_BLOCK_GRAD = 1, MCLIP_OP_PAIR_LSE = 2, MCLIP_OP_PAIR_REF = 3, MCLIP_OP_FUSED_GRAD = 4 };
+enum { MCLIP_OP_ROW_LSE = 0, MCLIP_OP_BLOCK_GRAD = 1, MCLIP_OP_PAIR_LSE = 2, MCLIP_OP_PAIR_REF = 3, MCLIP_OP_FUSED_GRAD = 4, MCLIP_OP_SMALL = 5 };
 enum {
   MCLIP_OK = 0,
   MCLIP_ERR_INVALID = 1,      /* bad shape / pointer / alignment / enum */
@@ -187,6 +187,35 @@ int mclip_normalize_rows_bwd(const float* x, const void* g, int64_t M, int64_t D
  * in *total_ms and their number in *count (either may be NULL); the record list is cleared.
  */
 int mclip_kernel_timing(int enable, float* total_ms, int* count);
+
+/*
+ * Latency path for small global batches (B_g <= 1024, D <= 512, D % 8 == 0, B_l * B_g <= 128 Ki; any of the three
+ * dtypes): the whole step is ONE forward and ONE backward kernel.  Every rank evaluates the full B_g x B_g problem, as the
+ * reference does for local_loss=False (loss.py:104-108), so only the feature gather crosses ranks: no statistics
+ * exchange, no scalar all-reduce.  fp32 FFMA arithmetic (fp32 inputs keep the 1e-5 bar).
+ *   A / B: image / text rows of ALL ranks in a blocked layout -- global row g lives at base + (g / Bl) * blk_stride +
+ *          (g % Bl) * D elements -- which is how the all-gather of [image shard; text shard] lands ([W][2][Bl][D]:
+ *          A = recv, B = recv + Bl * D, blk_stride = 2 * Bl * D); at world_size 1 A / B are the inputs themselves.
+ *   mclip_small_forward : stats[0..Bg) row LSEs, [Bg..2Bg) column LSEs, [2Bg..3Bg) positive-pair dots, [3Bg..4Bg) /
+ *          [4Bg..5Bg) softmax-weighted dots u / v, stats[5Bg] = loss = (1/(2n)) sum_{i in [lo,hi)} (row_lse + col_lse
+ *          - 2 ls diag)  (loss.py:142-145), stats[5Bg+1] = t = sum_{i in [lo,hi)} (u + v - 2 diag).
+ *   mclip_small_backward: for the rank's rows [off, off + Bl): dA = alpha G_A @ B_all, dB = alpha G_B @ A_all with
+ *          G = w_row P^row + w_col P^col - w_diag E and alpha = grad_out * logit_scale * inv_2n (the weights / n of the
+ *          mode table, as mclip_block_grad), and dls_out[0] = grad_out * dls_scale * t.
+ *   mclip_small_pack    : out = [a; b] converted to out_dtype (the all-gather's contiguous send buffer), n elements each.
+ * `counters`: mclip_small_counter_words() 32-bit words, zeroed once by the caller; every launch leaves them zeroed
+ * (last-CTA-done reductions inside the kernels).  Workspace: MCLIP_OP_SMALL with M = Bl, N = Bg.
+ */
+int mclip_small_supported(int64_t Bl, int64_t Bg, int64_t D, int dtype);
+int mclip_small_counter_words(int64_t Bl, int64_t Bg);
+int mclip_small_forward(const void* A, const void* B, int64_t Bl, int64_t Bg, int64_t D, int64_t blk_stride, int dtype,
+                        const float* logit_scale, int64_t lo, int64_t hi, float* stats, void* ws, size_t ws_bytes,
+                        unsigned* counters, void* cuda_stream);
+int mclip_small_backward(const void* A, const void* B, int64_t Bl, int64_t Bg, int64_t D, int64_t blk_stride, int dtype,
+                         const float* logit_scale, const float* grad_out, const float* stats, int64_t off, float w_row,
+                         float w_col, float w_diag, float inv_2n, float dls_scale, void* dA, void* dB, float* dls_out, void* ws,
+                         size_t ws_bytes, unsigned* counters, void* cuda_stream);
+int mclip_small_pack(const void* a, const void* b, int64_t n, int in_dtype, int out_dtype, void* out, void* cuda_stream);
 
 /*
  * Development / measurement switches.  Read from the environment once at load time (MCLIP_BWD_PERSIST, MCLIP_FUSED_BWD,

@@ -16,10 +16,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # MCLIP_LIB_PATH: development only (e.g. a -DMCLIP_PROFILE build next to the release library)
 LIB_PATH = os.environ.get("MCLIP_LIB_PATH") or os.path.join(_HERE, "libmclip_b200.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 DTYPE_CODES = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
 PATH_AUTO, PATH_SIMT, PATH_TCGEN05 = 0, 1, 2
-OP_ROW_LSE, OP_BLOCK_GRAD, OP_PAIR_LSE, OP_PAIR_REF, OP_FUSED_GRAD = 0, 1, 2, 3, 4
+OP_ROW_LSE, OP_BLOCK_GRAD, OP_PAIR_LSE, OP_PAIR_REF, OP_FUSED_GRAD, OP_SMALL = 0, 1, 2, 3, 4, 5
 
 _c_f32p = ctypes.c_void_p
 _SIGNATURES = {
@@ -51,6 +51,17 @@ _SIGNATURES = {
                                         _c_f32p, _c_f32p, _c_f32p, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p,
                                         ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, _c_f32p, ctypes.c_void_p,
                                         ctypes.c_size_t, ctypes.c_void_p]),
+    "mclip_small_supported": (ctypes.c_int, [ctypes.c_int64] * 3 + [ctypes.c_int]),
+    "mclip_small_counter_words": (ctypes.c_int, [ctypes.c_int64] * 2),
+    "mclip_small_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int64] * 4 + [ctypes.c_int, _c_f32p,
+                                           ctypes.c_int64, ctypes.c_int64, _c_f32p, ctypes.c_void_p, ctypes.c_size_t,
+                                           ctypes.c_void_p, ctypes.c_void_p]),
+    "mclip_small_backward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int64] * 4 + [ctypes.c_int, _c_f32p,
+                                            _c_f32p, _c_f32p, ctypes.c_int64] + [ctypes.c_float] * 5 +
+                             [ctypes.c_void_p, ctypes.c_void_p, _c_f32p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
+                              ctypes.c_void_p]),
+    "mclip_small_pack": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_void_p, ctypes.c_void_p]),
     "mclip_set_option": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int]),
     "mclip_get_option": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_int)]),
     "mclip_loss_finalize": (ctypes.c_int, [_c_f32p, _c_f32p, _c_f32p, ctypes.c_int64, _c_f32p, _c_f32p, ctypes.c_void_p]),
@@ -115,6 +126,8 @@ class CudaBackend:
         self._checked = set()
         self._ws_size = {}
         self._ws_buf = {}
+        self._counters = {}
+        self._small_ok = {}
 
     # -- helpers ---------------------------------------------------------------------------------
     def _prep(self, *tensors):
@@ -313,6 +326,62 @@ class CudaBackend:
                                            _ptr(dY), dY.stride(0), _ptr(xdot), _ptr(ws), nws, ctypes.c_void_p(stream))
         _check(self.lib, rc, "mclip_fused_grad")
         return dX, dY, xdot
+
+    # -- latency path (small global batches): one forward and one backward kernel per step -----------------------
+    def small_supported(self, Bl: int, Bg: int, D: int, dtype) -> bool:
+        if self.path != PATH_AUTO or dtype not in DTYPE_CODES or os.environ.get("MCLIP_NO_SMALL_PATH") == "1":
+            return False
+        key = (Bl, Bg, D, dtype)
+        ok = self._small_ok.get(key)
+        if ok is None:       # this sits on the per-step host path of the latency configuration: ask the library once per shape
+            ok = self._small_ok[key] = bool(self.lib.mclip_small_supported(Bl, Bg, D, DTYPE_CODES[dtype]))
+        return ok
+
+    def _small_counters(self, dev, stream_ptr):
+        """Persistent zeroed counter words per (device, stream): the kernels leave them zeroed after every launch."""
+        key = (dev.index, stream_ptr)
+        c = self._counters.get(key)
+        if c is None:
+            c = self._counters[key] = torch.zeros(128, dtype=torch.int32, device=dev)
+        return c
+
+    def small_pack(self, a, b, out_dtype):
+        """-> [2, Bl, D] contiguous send buffer (image shard, text shard) in the compute dtype."""
+        dev = self._prep(a, b)
+        out = torch.empty((2,) + tuple(a.shape), dtype=out_dtype, device=dev)
+        with self._DeviceGuard(dev):
+            rc = self.lib.mclip_small_pack(_ptr(a), _ptr(b), a.numel(), DTYPE_CODES[a.dtype], DTYPE_CODES[out_dtype], _ptr(out),
+                                           ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        _check(self.lib, rc, "mclip_small_pack")
+        return out
+
+    def small_forward(self, A, B, Bl, Bg, D, blk_stride, ls, lo, hi):
+        """-> stats [5 * Bg + 2] (row_lse, col_lse, diag, u, v, loss, t).  A / B: base tensors of the blocked layout."""
+        dev = self._prep(A, B, ls)
+        stats = torch.empty(5 * Bg + 2, dtype=torch.float32, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        ws, nws = self._workspace(Bl, Bg, D, A.dtype, OP_SMALL, dev, stream)
+        with self._DeviceGuard(dev):
+            rc = self.lib.mclip_small_forward(_ptr(A), _ptr(B), Bl, Bg, D, blk_stride, DTYPE_CODES[A.dtype], _ptr(ls), lo, hi,
+                                              _ptr(stats), _ptr(ws), nws, _ptr(self._small_counters(dev, stream)),
+                                              ctypes.c_void_p(stream))
+        _check(self.lib, rc, "mclip_small_forward")
+        return stats
+
+    def small_backward(self, A, B, Bl, Bg, D, blk_stride, ls, go, stats, off, w_row, w_col, w_diag, inv_2n, dls_scale):
+        """-> (dA [Bl, D], dB [Bl, D], dls [1])."""
+        dev = self._prep(A, B, ls, stats)
+        out = torch.empty((2, Bl, D), dtype=A.dtype, device=dev)
+        dls = torch.empty(1, dtype=torch.float32, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        ws, nws = self._workspace(Bl, Bg, D, A.dtype, OP_SMALL, dev, stream)
+        with self._DeviceGuard(dev):
+            rc = self.lib.mclip_small_backward(_ptr(A), _ptr(B), Bl, Bg, D, blk_stride, DTYPE_CODES[A.dtype], _ptr(ls), _ptr(go),
+                                               _ptr(stats), off, w_row, w_col, w_diag, inv_2n, dls_scale, _ptr(out[0]),
+                                               _ptr(out[1]), _ptr(dls), _ptr(ws), nws,
+                                               _ptr(self._small_counters(dev, stream)), ctypes.c_void_p(stream))
+        _check(self.lib, rc, "mclip_small_backward")
+        return out[0], out[1], dls
 
     def set_option(self, name: str, value: int) -> None:
         _check(self.lib, self.lib.mclip_set_option(name.encode(), int(value)), "mclip_set_option")

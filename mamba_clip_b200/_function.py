@@ -121,7 +121,44 @@ def _gather_into(out, x, group, comm=None):
         return dist.all_gather(list(out.chunk(dist.get_world_size(group), dim=0)), x, group=group, async_op=True)
 
 
-def _forward_impl(be, xi, xt, ls, local_loss, gather_with_grad, rank, W, group, need_ls, run=_EAGER, gathered=None):
+def _small_forward_impl(be, xi, xt, ls, local_loss, rank, W, group, run, send=None):
+    """Latency path (B_g <= 1024): [pack + ONE all-gather of (image shard; text shard)] + ONE forward kernel.  Every rank
+    evaluates the whole B_g x B_g problem, like the reference does for local_loss=False (loss.py:104-108): no statistics
+    exchange and no scalar all-reduce in either direction."""
+    Bl, D = xi.shape
+    Bg = W * Bl
+    dev = xi.device
+    if W > 1:
+        if send is None:       # (a producer that wrote xi / xt into one [2, Bl, D] buffer passes it: no pack kernel)
+            send = be.small_pack(xi, xt, xi.dtype)                     # [2, Bl, D]
+        recv = run.buffer("small_recv", (W, 2, Bl, D), xi.dtype, dev)
+        comm = _nccl.direct_comm(group, dev) if dev.type == "cuda" else None
+        _gather_into(recv.view(W, 2 * Bl * D), send.view(1, 2 * Bl * D), group, comm).wait()
+        A, Bm, stride, off = recv, recv[0, 1], 2 * Bl * D, int(rank) * Bl
+    else:
+        A, Bm, stride, off = xi, xt, Bl * D, 0
+    lo, hi = (off, off + Bl) if (W > 1 and local_loss) else (0, Bg)
+    stats = run.seg("small_fwd", lambda: be.small_forward(A, Bm, Bl, Bg, D, stride, ls, lo, hi))
+    return dict(small=True, loss=stats[5 * Bg:5 * Bg + 1].reshape(()), stats=stats, A=A, Bm=Bm, stride=stride, off=off, ls=ls, xi=xi, xt=xt)
+
+
+def _small_backward_impl(be, st, go, local_loss, gather_with_grad, W, need_ls, run):
+    Bl, D = st["xi"].shape
+    Bg = W * Bl
+    own_terms_only = W > 1 and local_loss and not gather_with_grad
+    w = (1.0, 0.0, 1.0) if own_terms_only else (1.0, 1.0, 2.0)
+    n_feat = Bg if (W == 1 or (not local_loss and not gather_with_grad)) else Bl
+    n_ls = Bl if (W > 1 and local_loss) else Bg
+    d_img, d_txt, d_ls = run.seg("small_bwd", lambda: be.small_backward(st["A"], st["Bm"], Bl, Bg, D, st["stride"], st["ls"], go,
+                                                                           st["stats"], st["off"], w[0], w[1], w[2],
+                                                                           1.0 / (2.0 * n_feat), 1.0 / (2.0 * n_ls)))
+    return d_img, d_txt, (d_ls[0] if need_ls else None)
+
+
+def _forward_impl(be, xi, xt, ls, local_loss, gather_with_grad, rank, W, group, need_ls, run=_EAGER, gathered=None,
+                  allow_small=False):
+    if allow_small and gathered is None:      # the caller has already asked be.small_supported(...)
+        return _small_forward_impl(be, xi, xt, ls, local_loss, rank, W, group, run)
     """Everything `ClipLoss.forward` launches, on already-cast contiguous inputs.  Returns the state dict that
     `_backward_impl` consumes.  Kernel launches are grouped into segments (`run.seg`) separated by the collectives:
     a segment is pure stream work without host synchronisation, so the graph runner can capture and replay it, while
@@ -229,6 +266,9 @@ def _backward_impl(be, st, go, local_loss, gather_with_grad, W, group, need_i, n
     """Everything `ClipLoss` launches in backward.  -> (d_image, d_text, d_logit_scale as a 0-dim f32 tensor).
     `rows = (lo, hi)`: only the local rows [lo, hi) need feature gradients (gradient accumulation: the other rows are
     cached, detached features of earlier micro-batches) -- the two recompute launches shrink to that row range."""
+    if st.get("small"):
+        d_img, d_txt, d_ls = _small_backward_impl(be, st, go, local_loss, gather_with_grad, W, need_ls, run)
+        return (d_img if need_i else None), (d_txt if need_t else None), d_ls
     xi, xt, all_i, all_t, ls = st["xi"], st["xt"], st["all_i"], st["all_t"], st["ls"]
     row_lse, col_lse, diag, off = st["row_lse"], st["col_lse"], st["diag"], st["off"]
     own_terms_only = st["own_terms_only"]
@@ -447,7 +487,10 @@ class ClipLossFunction(torch.autograd.Function):
         wants_grad = need_ls or image_features.requires_grad or text_features.requires_grad
 
         ctx.graphed = None
-        if (_GRAPHS_ENABLED and dev.type == "cuda" and _cabi._override is None
+        # the latency path is two kernels: replaying them from a graph would only add the static-buffer copies
+        small = (dev.type == "cuda" and _cabi._override is None
+                 and be.small_supported(xi.shape[0], W * xi.shape[0], xi.shape[1], cdt))
+        if (_GRAPHS_ENABLED and not small and dev.type == "cuda" and _cabi._override is None
                 and xi.shape[0] * xi.shape[0] * W * xi.shape[1] < _GRAPH_MAX_WORK
                 and not torch.cuda.is_current_stream_capturing()):
             key = (dev.index, tuple(xi.shape), cdt, bool(local_loss), bool(gather_with_grad), int(rank), W, id(group), need_ls)
@@ -469,11 +512,12 @@ class ClipLossFunction(torch.autograd.Function):
                 ctx.ls_meta = (logit_scale.dtype, logit_scale.shape, logit_scale.device) if torch.is_tensor(logit_scale) else None
                 return loss
 
-        st = _forward_impl(be, xi, xt, ls, bool(local_loss), bool(gather_with_grad), int(rank), W, group, need_ls)
+        st = _forward_impl(be, xi, xt, ls, bool(local_loss), bool(gather_with_grad), int(rank), W, group, need_ls, allow_small=small)
         loss = st.pop("loss")
-        # tensors go through save_for_backward (in-place modification checks); `stats` is written by an in-flight
-        # collective, so it is kept off autograd's version tracking together with the non-tensor state
-        ctx.save_for_backward(*(st.pop(k) for k in _SAVED_KEYS))
+        if not st.get("small"):
+            # tensors go through save_for_backward (in-place modification checks); `stats` is written by an in-flight
+            # collective, so it is kept off autograd's version tracking together with the non-tensor state
+            ctx.save_for_backward(*(st.pop(k) for k in _SAVED_KEYS))
         ctx.state = st
         ctx.cfg = (bool(local_loss), bool(gather_with_grad), W, group)
         ctx.in_dtypes = (image_features.dtype, text_features.dtype)
@@ -497,7 +541,8 @@ class ClipLossFunction(torch.autograd.Function):
             gl.pending = False   # (a second backward through retain_graph stays valid until the next forward)
         else:
             st = dict(ctx.state)
-            st.update(zip(_SAVED_KEYS, ctx.saved_tensors))
+            if not st.get("small"):
+                st.update(zip(_SAVED_KEYS, ctx.saved_tensors))
             go = grad_out.detach().to(device=st["xi"].device, dtype=torch.float32).reshape(1).contiguous()
             d_img, d_txt, d_ls = _backward_impl(be, st, go, local_loss, gather_with_grad, W, group, need_i, need_t, need_ls)
         if d_ls is not None:
@@ -526,19 +571,29 @@ class ClipLossFromProjectionsFunction(torch.autograd.Function):
         Bl, D = pi.shape
         W = int(world_size)
         off = int(rank) * Bl if W > 1 else 0
-        all_i = torch.empty((W * Bl, D), dtype=dtype, device=dev)
-        all_t = torch.empty((W * Bl, D), dtype=dtype, device=dev)
-        xi = be.normalize_rows(pi, dtype, eps, out=all_i[off:off + Bl])
-        xt = be.normalize_rows(pt, dtype, eps, out=all_t[off:off + Bl])
         if torch.is_tensor(logit_scale):
             ls = logit_scale.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
         else:
             ls = torch.full((1,), float(logit_scale), dtype=torch.float32, device=dev)
         need_ls = torch.is_tensor(logit_scale) and logit_scale.requires_grad
-        st = _forward_impl(be, xi, xt, ls, bool(local_loss), bool(gather_with_grad), int(rank), W, group, need_ls,
-                           gathered=(all_i, all_t) if W > 1 else None)
+        if be.small_supported(Bl, W * Bl, D, dtype):
+            # latency path: normalise straight into the [image shard; text shard] send buffer of its single all-gather
+            send = torch.empty((2, Bl, D), dtype=dtype, device=dev)
+            xi = be.normalize_rows(pi, dtype, eps, out=send[0])
+            xt = be.normalize_rows(pt, dtype, eps, out=send[1])
+            st = _small_forward_impl(be, xi, xt, ls, bool(local_loss), int(rank), W, group, _EAGER, send=send)
+        else:
+            all_i = torch.empty((W * Bl, D), dtype=dtype, device=dev)
+            all_t = torch.empty((W * Bl, D), dtype=dtype, device=dev)
+            xi = be.normalize_rows(pi, dtype, eps, out=all_i[off:off + Bl])
+            xt = be.normalize_rows(pt, dtype, eps, out=all_t[off:off + Bl])
+            st = _forward_impl(be, xi, xt, ls, bool(local_loss), bool(gather_with_grad), int(rank), W, group, need_ls,
+                               gathered=(all_i, all_t) if W > 1 else None)
         loss = st.pop("loss")
-        ctx.save_for_backward(pi, pt, *(st.pop(k) for k in _SAVED_KEYS))
+        if st.get("small"):
+            ctx.save_for_backward(pi, pt)
+        else:
+            ctx.save_for_backward(pi, pt, *(st.pop(k) for k in _SAVED_KEYS))
         ctx.state = st
         ctx.eps = eps
         ctx.cfg = (bool(local_loss), bool(gather_with_grad), W, group)
@@ -555,7 +610,8 @@ class ClipLossFromProjectionsFunction(torch.autograd.Function):
         need_ls = need_ls and ctx.ls_meta is not None
         pi, pt, *saved = ctx.saved_tensors
         st = dict(ctx.state)
-        st.update(zip(_SAVED_KEYS, saved))
+        if not st.get("small"):
+            st.update(zip(_SAVED_KEYS, saved))
         go = grad_out.detach().to(device=pi.device, dtype=torch.float32).reshape(1).contiguous()
         d_img, d_txt, d_ls = _backward_impl(be, st, go, local_loss, gather_with_grad, W, group, need_i, need_t, need_ls)
         if d_img is not None:

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmclip_b200.so")
-SOURCES = ["abi.cu", "simt_kernels.cu", "tc_kernels.cu", "tc_pair_lse.cu", "tc_gemm_tn.cu", "producer_kernels.cu"]
+SOURCES = ["abi.cu", "simt_kernels.cu", "small_kernels.cu", "tc_kernels.cu", "tc_pair_lse.cu", "tc_gemm_tn.cu", "producer_kernels.cu"]
 HEADERS = ["common.cuh", "sm100_ptx.cuh", "tc_host.cuh", os.path.join("..", "..", "include", "mclip_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -85,6 +85,7 @@ int mclip_workspace_bytes(int64_t M, int64_t N, int64_t D, int dtype, int op, in
   else if (op == MCLIP_OP_PAIR_LSE) { *bytes = tc_pair_lse_ws(M, N, D); return MCLIP_OK; }
   else if (op == MCLIP_OP_PAIR_REF) { *bytes = pair_ref_ws(); return MCLIP_OK; }
   else if (op == MCLIP_OP_FUSED_GRAD) { *bytes = tc_fused_grad_ws(M, N, D); return MCLIP_OK; }
+  else if (op == MCLIP_OP_SMALL) { *bytes = small_ws_bytes(M, N, D); return MCLIP_OK; }
   else { set_error("workspace_bytes: bad op %d", op); return MCLIP_ERR_INVALID; }
   if (path == MCLIP_PATH_SIMT) *bytes = simt;
   else if (path == MCLIP_PATH_TCGEN05) *bytes = tc;
@@ -202,6 +203,55 @@ int mclip_fused_grad(const void* X, const void* Y, int64_t M, int64_t N, int64_t
   FusedGradArgs a{X, Y, M, N, D, ldx, ldy, dtype, logit_scale, grad_out, lse_x, lse_y, diag_off, inv_2n, dX, lddx, dY, lddy, xdot,
                   ws, ws_bytes, (cudaStream_t)cuda_stream};
   return tc_fused_grad(a);
+}
+
+int mclip_small_supported(int64_t Bl, int64_t Bg, int64_t D, int dtype) {
+  return (valid_dtype(dtype) && small_supported(Bl, Bg, D)) ? 1 : 0;
+}
+
+int mclip_small_counter_words(int64_t Bl, int64_t Bg) { return small_counter_words(Bl, Bg); }
+
+static int check_small(const void* A, const void* B, int64_t Bl, int64_t Bg, int64_t D, int64_t blk_stride, int dtype,
+                       const float* ls, const float* stats, const void* ws, size_t ws_bytes, const unsigned* counters, const char* op) {
+  if (!A || !B || !ls || !stats || !counters) { set_error("%s: null pointer", op); return MCLIP_ERR_INVALID; }
+  if (!valid_dtype(dtype) || !small_supported(Bl, Bg, D)) { set_error("%s: unsupported problem Bl=%lld Bg=%lld D=%lld", op, (long long)Bl, (long long)Bg, (long long)D); return MCLIP_ERR_UNSUPPORTED; }
+  if (Bg > Bl && blk_stride < Bl * D) { set_error("%s: blk_stride smaller than one shard", op); return MCLIP_ERR_INVALID; }
+  if ((((uintptr_t)A) | ((uintptr_t)B)) & 15) { set_error("%s: A/B must be 16-byte aligned", op); return MCLIP_ERR_INVALID; }
+  const size_t need = small_ws_bytes(Bl, Bg, D);
+  if (!ws || ws_bytes < need) { set_error("%s: workspace %zu < %zu bytes", op, ws_bytes, need); return MCLIP_ERR_WORKSPACE; }
+  return MCLIP_OK;
+}
+
+int mclip_small_forward(const void* A, const void* B, int64_t Bl, int64_t Bg, int64_t D, int64_t blk_stride, int dtype,
+                        const float* logit_scale, int64_t lo, int64_t hi, float* stats, void* ws, size_t ws_bytes,
+                        unsigned* counters, void* cuda_stream) {
+  int rc = check_small(A, B, Bl, Bg, D, blk_stride, dtype, logit_scale, stats, ws, ws_bytes, counters, "small_forward");
+  if (rc) return rc;
+  if (lo < 0 || hi > Bg || lo >= hi) { set_error("small_forward: bad row range [%lld, %lld)", (long long)lo, (long long)hi); return MCLIP_ERR_INVALID; }
+  SmallArgs a{};
+  a.A = A; a.B = B; a.Bl = Bl; a.Bg = Bg; a.D = D; a.blk_stride = blk_stride; a.dtype = dtype; a.logit_scale = logit_scale;
+  a.lo = lo; a.hi = hi; a.stats = stats; a.ws = ws; a.ws_bytes = ws_bytes; a.counters = counters; a.stream = (cudaStream_t)cuda_stream;
+  return small_forward(a);
+}
+
+int mclip_small_backward(const void* A, const void* B, int64_t Bl, int64_t Bg, int64_t D, int64_t blk_stride, int dtype,
+                         const float* logit_scale, const float* grad_out, const float* stats, int64_t off, float w_row,
+                         float w_col, float w_diag, float inv_2n, float dls_scale, void* dA, void* dB, float* dls_out, void* ws,
+                         size_t ws_bytes, unsigned* counters, void* cuda_stream) {
+  int rc = check_small(A, B, Bl, Bg, D, blk_stride, dtype, logit_scale, stats, ws, ws_bytes, counters, "small_backward");
+  if (rc) return rc;
+  if (!dA || !dB || off < 0 || off + Bl > Bg) { set_error("small_backward: null outputs or bad row offset"); return MCLIP_ERR_INVALID; }
+  SmallArgs a{};
+  a.A = A; a.B = B; a.Bl = Bl; a.Bg = Bg; a.D = D; a.blk_stride = blk_stride; a.dtype = dtype; a.logit_scale = logit_scale;
+  a.stats = const_cast<float*>(stats); a.off = off; a.grad_out = grad_out; a.w_row = w_row; a.w_col = w_col; a.w_diag = w_diag;
+  a.inv_2n = inv_2n; a.dls_scale = dls_scale; a.dA = dA; a.dB = dB; a.dls_out = dls_out; a.ws = ws; a.ws_bytes = ws_bytes;
+  a.counters = counters; a.stream = (cudaStream_t)cuda_stream;
+  return small_backward(a);
+}
+
+int mclip_small_pack(const void* a, const void* b, int64_t n, int in_dtype, int out_dtype, void* out, void* cuda_stream) {
+  if (!a || !b || !out || n <= 0 || !valid_dtype(in_dtype) || !valid_dtype(out_dtype)) { set_error("small_pack: invalid argument"); return MCLIP_ERR_INVALID; }
+  return small_pack(a, b, n, in_dtype, out_dtype, out, (cudaStream_t)cuda_stream);
 }
 
 int mclip_set_option(const char* name, int value) { return tc_set_option(name, value); }

@@ -108,6 +108,30 @@ struct FusedGradArgs {
   cudaStream_t stream;
 };
 
+// latency path for small global batches (small_kernels.cu): one forward and one backward kernel per step
+struct SmallArgs {
+  const void* A; const void* B;   // image / text rows in the blocked layout: row g at base + (g / Bl) * blk_stride + (g % Bl) * D
+  int64_t Bl, Bg, D, blk_stride;
+  int dtype;
+  const float* logit_scale;
+  int64_t lo, hi;                 // forward: rows whose loss / t terms are summed
+  float* stats;                   // [5 * Bg + 2]: row_lse, col_lse, diag, u, v, then loss, t
+  // backward only
+  int64_t off;                    // first global row of this rank
+  const float* grad_out;
+  float w_row, w_col, w_diag, inv_2n, dls_scale;
+  void* dA; void* dB; float* dls_out;
+  void* ws; size_t ws_bytes;
+  unsigned* counters;             // zero-initialised by the caller once; every launch leaves it zeroed
+  cudaStream_t stream;
+};
+bool small_supported(int64_t Bl, int64_t Bg, int64_t D);
+size_t small_ws_bytes(int64_t Bl, int64_t Bg, int64_t D);
+int small_counter_words(int64_t Bl, int64_t Bg);
+int small_forward(const SmallArgs& a);
+int small_backward(const SmallArgs& a);
+int small_pack(const void* a, const void* b, int64_t n, int in_dtype, int out_dtype, void* out, cudaStream_t stream);
+
 // SIMT (FFMA, fp32-exact) path -- simt_kernels.cu
 size_t simt_row_lse_ws(int64_t M, int64_t N, int64_t D);
 int simt_row_lse(const RowLseArgs& a);

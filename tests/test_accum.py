@@ -85,7 +85,8 @@ def test_accum_on_gpu(accum, B, D, dtype, tol):
         s2 = torch.tensor(ls, device="cuda", requires_grad=True)
         l2 = crit(fi, ft, s2, output_dict=False)
         l2.backward()
-        assert float(l2.detach()) == float(loss.detach())           # same forward launches
+        # (same forward launches on the general path; sizes that qualify for the latency path sum in another order)
+        assert abs(float(l2.detach()) - float(loss.detach())) <= 2e-6 * abs(float(loss.detach()))
         # the recompute launch over a row subset may pick another column split, i.e. another f32 summation order
         assert O.rel_err(a.grad.float().cpu(), fi.grad[lo:hi].float().cpu()) <= 5e-4
         assert O.rel_err(b.grad.float().cpu(), ft.grad[lo:hi].float().cpu()) <= 5e-4

@@ -59,6 +59,11 @@ def _worker(rank, W, port, jobs, q):
             # "graphs": the step is repeated so that the last repetition replays the captured CUDA graphs (collectives
             # included); every repetition must give the same result
             mamba_clip_b200.enable_cuda_graphs(bool(job.get("graphs")))
+            # "no_small": keep the job on the general (tensor-core) path although its size qualifies for the latency path
+            if job.get("no_small"):
+                os.environ["MCLIP_NO_SMALL_PATH"] = "1"
+            else:
+                os.environ.pop("MCLIP_NO_SMALL_PATH", None)
             reps = 5 if job.get("graphs") else 1
             Bl, D = job["Bl"], job["D"]
             dtype = getattr(torch, job["dtype"])
@@ -132,12 +137,16 @@ def test_nccl_bf16_tensor_core_sizes_against_oracle(W):
     for local_loss in (False, True):
         for gwg in (False, True):
             jobs.append(dict(Bl=256, D=512, dtype="bfloat16", seed=77, corr=True, ls=20.0, go=2.0,
-                             local_loss=local_loss, gwg=gwg))
+                             local_loss=local_loss, gwg=gwg, no_small=True))
+            jobs.append(dict(Bl=64, D=512, dtype="bfloat16", seed=177, corr=True, ls=20.0, go=2.0,
+                             local_loss=local_loss, gwg=gwg))            # latency path (C2's per-rank shape)
     jobs.append(dict(Bl=256, D=512, dtype="bfloat16", seed=78, corr=True, ls=100.0, go=2.0, local_loss=True, gwg=True,
-                     adv=True))
+                     adv=True, no_small=True))
     for local_loss, gwg in ((True, True), (False, False)):
         jobs.append(dict(Bl=256, D=512, dtype="bfloat16", seed=79, corr=True, ls=20.0, go=2.0, local_loss=local_loss, gwg=gwg,
-                         graphs=True))
+                         graphs=True, no_small=True))
+        jobs.append(dict(Bl=64, D=512, dtype="bfloat16", seed=179, corr=True, ls=20.0, go=2.0, local_loss=local_loss, gwg=gwg,
+                         graphs=True))                                   # latency path replayed from CUDA graphs
     out = _run(W, jobs)
     for j, job in enumerate(jobs):
         img, txt = _features(W, job)
@@ -169,9 +178,11 @@ def test_nccl_two_ranks_ragged_shapes_and_forced_fallback():
     for Bl, D in ((200, 96), (300, 200), (1000, 512), (200, 512), (1000, 96)):
         for local_loss, gwg in ((True, True), (False, False), (True, False)):
             jobs.append(dict(Bl=Bl, D=D, dtype="bfloat16", seed=100 + Bl + D, corr=True, ls=20.0, go=2.0,
-                             local_loss=local_loss, gwg=gwg))
-    jobs.append(dict(Bl=300, D=200, dtype="bfloat16", seed=5, corr=True, ls=100.0, go=2.0, local_loss=True, gwg=True, adv=True))
+                             local_loss=local_loss, gwg=gwg, no_small=True))
+    jobs.append(dict(Bl=300, D=200, dtype="bfloat16", seed=5, corr=True, ls=100.0, go=2.0, local_loss=True, gwg=True, adv=True,
+                     no_small=True))
     jobs.append(dict(Bl=1000, D=96, dtype="float16", seed=6, corr=True, ls=100.0, go=1.0, local_loss=False, gwg=True, adv=True))
+    jobs.append(dict(Bl=200, D=96, dtype="bfloat16", seed=8, corr=True, ls=20.0, go=2.0, local_loss=False, gwg=False))   # latency path, ragged
     out = _run(W, jobs)
     for j, job in enumerate(jobs):
         img, txt = _features(W, job)

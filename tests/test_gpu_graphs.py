@@ -27,7 +27,7 @@ def _step(crit, img, txt, ls_val, go=1.0):
     return float(loss.detach()), a.grad.clone(), b.grad.clone(), float(s.grad)
 
 
-@pytest.mark.parametrize("B,D,dtype", [(1024, 512, torch.bfloat16), (300, 200, torch.bfloat16), (256, 96, torch.float32)])
+@pytest.mark.parametrize("B,D,dtype", [(1024, 512, torch.bfloat16), (400, 200, torch.bfloat16), (512, 96, torch.float32)])
 def test_graph_replay_equals_eager(graphs, B, D, dtype):
     import mamba_clip_b200 as M
     from mamba_clip_b200 import ClipLoss

@@ -310,10 +310,15 @@ def projector(dim):
 Z, CASES = load_single()
 
 
+@pytest.mark.parametrize("small", [True, False], ids=["latency-path", "general-path"])
 @pytest.mark.parametrize("k", range(len(CASES)))
-def test_clip_loss_against_reference_golden(k):
-    """ClipLoss (W=1) on the GPU vs the outputs of the real reference ClipLoss (tests/golden)."""
+def test_clip_loss_against_reference_golden(k, small, monkeypatch):
+    """ClipLoss (W=1) on the GPU vs the outputs of the real reference ClipLoss (tests/golden), once through whatever path
+    the size selects (the one-forward-one-backward-kernel latency path for B_g <= 1024) and once with that path switched
+    off, so that the general kernels keep their coverage at small shapes."""
     from mamba_clip_b200 import ClipLoss
+    if not small:
+        monkeypatch.setenv("MCLIP_NO_SMALL_PATH", "1")
     case = CASES[k]
     img, txt = O.make_features(case["B"], case["D"], seed=case["seed"], correlated=case["corr"])
     dtype = torch.bfloat16 if case["bf16"] else torch.float32
@@ -441,6 +446,17 @@ def test_launch_counter_moves():
     img, txt = O.make_features(64, 64, seed=1, dtype=torch.bfloat16)
     a = img.cuda().requires_grad_(True)
     ClipLoss()(a, txt.cuda(), torch.tensor(10.0, device="cuda"), output_dict=False).backward()
+    assert be.launch_count() - n0 == 2          # latency path: one forward kernel, one backward kernel
+
+
+def test_general_path_launch_counter(monkeypatch):
+    from mamba_clip_b200 import ClipLoss, _cabi
+    monkeypatch.setenv("MCLIP_NO_SMALL_PATH", "1")
+    be = _cabi.get_backend()
+    n0 = be.launch_count()
+    img, txt = O.make_features(64, 64, seed=1, dtype=torch.bfloat16)
+    a = img.cuda().requires_grad_(True)
+    ClipLoss()(a, txt.cuda(), torch.tensor(10.0, device="cuda"), output_dict=False).backward()
     assert be.launch_count() - n0 >= 6
 
 
@@ -557,3 +573,69 @@ def test_clip_loss_at_headline_size_against_closed_form(B, D, ls, corr):
     assert e_di <= tol * float(r_di.norm()) + g_floor
     assert e_dt <= tol * float(r_dt.norm()) + g_floor
     assert e_dls <= tol * abs(float(r_dls)) + d_floor
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# latency path (mclip_small_forward / mclip_small_backward): the primitives against the fp64 oracle
+# ---------------------------------------------------------------------------------------------------------------------
+SMALL_CASES = [
+    # (dtype, W, Bl, D, ls, (local_loss, gwg))
+    (torch.float32, 1, 64, 512, 14.2857, (False, False)),
+    (torch.float32, 1, 7, 8, 5.0, (False, False)),
+    (torch.bfloat16, 1, 256, 512, 100.0, (False, False)),
+    (torch.bfloat16, 8, 64, 512, 14.2857, (False, False)),       # C2
+    (torch.bfloat16, 8, 64, 512, 20.0, (True, True)),
+    (torch.float16, 4, 100, 96, 30.0, (True, False)),
+    (torch.float32, 2, 130, 200, 20.0, (False, True)),
+    (torch.bfloat16, 16, 64, 256, 14.2857, (False, False)),
+]
+
+
+@pytest.mark.parametrize("dtype,W,Bl,D,ls,mode", SMALL_CASES,
+                         ids=[f"{str(c[0]).split('.')[-1]}-W{c[1]}-{c[2]}x{c[3]}-{int(c[5][0])}{int(c[5][1])}" for c in SMALL_CASES])
+def test_small_path_primitives_every_rank(dtype, W, Bl, D, ls, mode):
+    """One process plays every rank in turn: the blocked layout [W][2][Bl][D] is what the all-gather of the packed shards
+    produces; loss, dA, dB, d(logit_scale) of each rank against the oracle's rank emulation (the reference's semantics)."""
+    be = backend(0)
+    local_loss, gwg = mode
+    Bg = W * Bl
+    assert be.small_supported(Bl, Bg, D, dtype)
+    img, txt = O.make_features(Bg, D, seed=7 * W + Bl, correlated=True, dtype=dtype)
+    ref = O.ref_port_ranks(img.float(), txt.float(), ls, W, local_loss, gwg, grad_output=2.0)
+    lsd = torch.tensor([ls], device="cuda")
+    go = torch.tensor([2.0], device="cuda")
+    if W > 1:
+        recv = torch.stack([torch.stack((img[r * Bl:(r + 1) * Bl], txt[r * Bl:(r + 1) * Bl])) for r in range(W)]).cuda()
+        A, Bm, stride = recv, recv[0, 1], 2 * Bl * D
+    else:
+        A, Bm, stride = img.cuda(), txt.cuda(), Bl * D
+    tol = TOL[dtype]
+    own_only = W > 1 and local_loss and not gwg
+    w = (1.0, 0.0, 1.0) if own_only else (1.0, 1.0, 2.0)
+    n_feat = Bg if (W == 1 or (not local_loss and not gwg)) else Bl
+    n_ls = Bl if (W > 1 and local_loss) else Bg
+    for r in range(W):
+        off = r * Bl
+        lo, hi = (off, off + Bl) if (W > 1 and local_loss) else (0, Bg)
+        stats = be.small_forward(A, Bm, Bl, Bg, D, stride, lsd, lo, hi)
+        dA, dB, dls = be.small_backward(A, Bm, Bl, Bg, D, stride, lsd, go, stats, off, *w, 1.0 / (2 * n_feat), 1.0 / (2 * n_ls))
+        torch.cuda.synchronize()
+        loss = float(stats[5 * Bg])
+        sat = ls >= 100.0
+        assert abs(loss - float(ref[r].loss)) <= tol * abs(float(ref[r].loss)) + (4 * 1.2e-7 * ls if sat else 2e-6)
+        floor = 8 * 1.2e-7 * max(1.0, ls) * 2.0 * ls / (2 * n_feat) * Bl ** 0.5
+        for got, want in ((dA, ref[r].d_image), (dB, ref[r].d_text)):
+            assert float((got.cpu().double() - want.double()).norm()) <= tol * float(want.double().norm()) + floor
+        d_floor = 1.2e-7 * 2.0 * max(1.0, ls) * (20 if dtype != torch.float32 else 4)
+        assert abs(float(dls) - float(ref[r].d_logit_scale)) <= tol * abs(float(ref[r].d_logit_scale)) + d_floor
+    # the launches leave the counter words zeroed: a second identical call reproduces the result bit for bit
+    stats2 = be.small_forward(A, Bm, Bl, Bg, D, stride, lsd, lo, hi)
+    assert torch.equal(stats, stats2)
+
+
+def test_small_pack_concatenates_and_casts():
+    be = backend(0)
+    a = torch.randn(64, 512, device="cuda")
+    b = torch.randn(64, 512, device="cuda")
+    out = be.small_pack(a, b, torch.bfloat16)
+    assert out.shape == (2, 64, 512) and torch.equal(out[0], a.bfloat16()) and torch.equal(out[1], b.bfloat16())
