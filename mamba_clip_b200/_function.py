@@ -133,7 +133,13 @@ def _small_forward_impl(be, xi, xt, ls, local_loss, rank, W, group, run, send=No
             send = be.small_pack(xi, xt, xi.dtype)                     # [2, Bl, D]
         recv = run.buffer("small_recv", (W, 2, Bl, D), xi.dtype, dev)
         comm = _nccl.direct_comm(group, dev) if dev.type == "cuda" else None
-        _gather_into(recv.view(W, 2 * Bl * D), send.view(1, 2 * Bl * D), group, comm).wait()
+        if comm is not None:
+            # pack -> gather -> forward kernel are strictly dependent: issue the gather in order on the compute stream
+            # (no stream hop, no events).  The general path's communication stream always waits for the compute stream
+            # before its own collectives, so calls of the one communicator stay totally ordered across the two paths.
+            comm.all_gather(recv.view(W, 2 * Bl * D), send.view(1, 2 * Bl * D))
+        else:
+            _gather_into(recv.view(W, 2 * Bl * D), send.view(1, 2 * Bl * D), group, None).wait()
         A, Bm, stride, off = recv, recv[0, 1], 2 * Bl * D, int(rank) * Bl
     else:
         A, Bm, stride, off = xi, xt, Bl * D, 0
