@@ -81,7 +81,7 @@ int mclip_row_lse(const void* X, const void* Y, int64_t M, int64_t N, int64_t D,
  * mclip_merge_col_sums (or a single vector with mclip_lse_from_sum).  Validity is checked on the result: if any row / column total leaves
  * [2^-75, 2^120] the call ORs a non-zero bit into *status (device int) and the outputs must be recomputed by
  * mclip_row_lse(..., run_if = status).  tcgen05 path only: mclip_pair_supported() says whether a problem qualifies
- * (bf16/f16, D % 8 == 0, D <= 512, leading dimensions % 8 == 0).
+ * (bf16/f16, D % 8 == 0, D <= 768, leading dimensions % 8 == 0; for 512 < D the k-chunks past 512 of the row block are streamed).
  * `diag` (may be NULL; otherwise the vector mclip_pair_ref filled, same diag_off) is overwritten with the tensor-core
  * accumulator's own <X[i], Y[i + diag_off]>: with a saturated softmax the loss subtracts logit_scale * diag from an LSE
  * dominated by that same product, so both must carry identical rounding.

@@ -132,7 +132,7 @@ int mclip_pair_lse(const void* X, const void* Y, int64_t M, int64_t N, int64_t D
   if (!ref || !row_lse || !col_out || !status) { set_error("pair_lse: null ref/row_lse/col_out/status"); return MCLIP_ERR_INVALID; }
   if (col_mode != 0 && col_mode != 1) { set_error("pair_lse: bad col_mode %d", col_mode); return MCLIP_ERR_INVALID; }
   if (!tc_pair_supported(M, N, D, ldx, ldy, dtype)) {
-    set_error("pair_lse: needs bf16/f16, D %% 8 == 0, D <= 512, ld %% 8 == 0");
+    set_error("pair_lse: needs bf16/f16, D %% 8 == 0, D <= 768, ld %% 8 == 0");
     return MCLIP_ERR_UNSUPPORTED;
   }
   const size_t need = tc_pair_lse_ws(M, N, D);

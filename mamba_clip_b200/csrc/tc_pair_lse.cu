@@ -179,12 +179,24 @@ tc_pair_lse2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       uint32_t it = 0;
       for (int t = t0; t < t1; ++t) {
         const int32_t y0 = t * BN + 128 * (int32_t)rank;     // this CTA's half of the tile's Y rows
-        for (int c = 0; c < p.kch; ++c, ++it) {
+        for (int c = 0; c < p.kch; ++c) {
+          if (c >= 8) {
+            // 512 < D <= 768: only the first 8 k-chunks of the X block are resident (128 KB); chunks 8..11 travel through
+            // the ring in front of their Y chunk, once per column tile (+33 % ring traffic: 42 B/clk/SM, under the
+            // ingest limit that the streamed-everything single-CTA kernel sits on)
+            const int s = it % kStages;
+            const uint32_t ph = (it / kStages) & 1;
+            mbar_wait(empty_bar(s), ph ^ 1);
+            if (leader) mbar_expect_tx(full_bar(s), 2 * kChunkBytes); else mbar_arrive_cluster(full_bar(s), 0);
+            tma_load_2d_cg2(ring_base + s * kChunkBytes, &tmX, c * 64, (int32_t)m0, full_bar(s));
+            ++it;
+          }
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
           mbar_wait(empty_bar(s), ph ^ 1);
           if (leader) mbar_expect_tx(full_bar(s), 2 * kChunkBytes); else mbar_arrive_cluster(full_bar(s), 0);
           tma_load_2d_cg2(ring_base + s * kChunkBytes, &tmY, c * 64, y0, full_bar(s));
+          ++it;
         }
       }
     }
@@ -200,13 +212,21 @@ tc_pair_lse2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         mbar_wait(tempty_bar(buf), bph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * BN;
-        for (int c = 0; c < p.kch; ++c, ++it) {
+        for (int c = 0; c < p.kch; ++c) {
+          uint32_t a_addr = smem_base + c * kChunkBytes;
+          int sx = -1;
+          if (c >= 8) {                      // streamed X chunk (see the producer)
+            sx = it % kStages;
+            mbar_wait(full_bar(sx), (it / kStages) & 1);
+            a_addr = ring_base + sx * kChunkBytes;
+            ++it;
+          }
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
+          ++it;
           const uint32_t b_addr = ring_base + s * kChunkBytes;
-          const uint32_t a_addr = smem_base + c * kChunkBytes;
           if (elected) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -214,6 +234,7 @@ tc_pair_lse2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
               const uint64_t bd = make_smem_desc_sw128(b_addr + k * 32, 0, 1024);
               mma_ss_cg2(d_tmem, ad, bd, idesc, (c | k) != 0);
             }
+            if (sx >= 0) mma_commit_cg2(empty_bar(sx), 3);
             mma_commit_cg2(empty_bar(s), 3);
             if (c == p.kch - 1) mma_commit_cg2(tfull_bar(buf), 3);
           }
@@ -525,7 +546,7 @@ PairWs pair_ws_layout(const PairPlan& f, int64_t M) {
 bool tc_pair_supported(int64_t M, int64_t N, int64_t D, int64_t ldx, int64_t ldy, int dtype) {
   (void)M; (void)N;
   if (dtype != MCLIP_DTYPE_BF16 && dtype != MCLIP_DTYPE_F16) return false;
-  if (D % 8 != 0 || D > 512) return false;
+  if (D % 8 != 0 || D > 768) return false;
   if (ldx % 8 != 0 || ldy % 8 != 0) return false;
   return true;
 }

@@ -164,6 +164,11 @@ PAIR_CASES = [
     (torch.bfloat16, 1000, 5000, 512, 40.0, 1024, True),
     (torch.bfloat16, 384, 640, 128, -12.0, 0, True),     # negative scale
     (torch.bfloat16, 4096, 4096, 512, 100.0, 0, True),   # saturated, all positives near the maximum
+    # 512 < D <= 768: k-chunks 8..11 of the X block are streamed through the ring in front of their Y chunk
+    (torch.bfloat16, 256, 512, 768, 14.2857, 0, True),
+    (torch.float16, 300, 1000, 640, 25.0, 17, True),
+    (torch.bfloat16, 2048, 4096, 768, 30.0, 1024, False),
+    (torch.bfloat16, 1000, 3000, 520, 20.0, 0, True),
 ]
 
 
