@@ -66,6 +66,11 @@ class ClipLoss(torch.nn.Module):
 
     No parameters or buffers (checkpoints are unaffected).  `forward` returns
     `{"contrastive_loss": loss}` by default, like the reference (`output_dict=True`).
+
+    Input contract (the producer's, reference model.py:1011-1017): features are L2-normalised rows.  Arbitrary finite
+    features are accepted and the loss value is exact for them, but for **bf16** inputs the backward multiplies with an f16
+    copy of the features (exact for 6.1e-5 <= |v| <= 65504; saturating above), so bf16 features beyond +-65504 would see
+    clamped gradients.  fp16 and fp32 inputs have no such restriction.  `backward` is once-differentiable.
     """
 
     def __init__(self, local_loss=False, gather_with_grad=False, cache_labels=False, rank=0, world_size=1):

@@ -60,7 +60,21 @@ def test_argument_validation_without_gpu(lib):
     assert lib.mclip_merge_col_sums(None, 2, 10, 8, 0, 4, None, None, None) == 1
     assert lib.mclip_lse_from_sum(None, 4, None, None, None, None) == 1
     assert lib.mclip_pair_supported(4096, 4096, 512, 512, 512, 1) == 1        # bf16, D <= 512
-    assert lib.mclip_pair_supported(4096, 4096, 768, 768, 768, 1) == 0        # D > 512: one-sided kernels
+    assert lib.mclip_pair_supported(4096, 4096, 768, 768, 768, 1) == 1        # 512 < D <= 768: X k-chunks past 512 streamed
+    assert lib.mclip_pair_supported(4096, 4096, 832, 832, 832, 1) == 0        # D > 768: one-sided kernels
+    # round-2 entry points: argument validation, support queries, options (no GPU work)
+    assert lib.mclip_fused_grad(None, None, 4096, 8192, 512, 512, 512, 1, None, None, None, None, 0, 0.5, None, 512, None, 512,
+                                None, None, 0, None) == 1
+    assert lib.mclip_small_supported(64, 512, 512, 1) == 1 and lib.mclip_small_supported(64, 2048, 512, 1) == 0
+    assert lib.mclip_small_supported(64, 512, 520, 0) == 0 and lib.mclip_small_supported(64, 64, 512, 0) == 1
+    assert lib.mclip_small_counter_words(64, 512) >= 17
+    assert lib.mclip_small_forward(None, None, 64, 512, 512, 65536, 1, None, 0, 512, None, None, 0, None, None) == 1
+    assert lib.mclip_small_pack(None, None, 10, 1, 1, None, None) == 1
+    assert lib.mclip_set_option(b"no_such_option", 1) == 1
+    import ctypes as _ct
+    v = _ct.c_int(-1)
+    assert lib.mclip_set_option(b"bwd_persist", 1) == 0 and lib.mclip_get_option(b"bwd_persist", _ct.byref(v)) == 0 and v.value == 1
+    assert lib.mclip_set_option(b"bwd_persist", 0) == 0
     assert lib.mclip_pair_supported(4096, 4096, 512, 512, 512, 0) == 0        # fp32: FFMA path
     for op in (2, 3):                                                          # PAIR_LSE, PAIR_REF workspaces
         assert lib.mclip_workspace_bytes(32768, 32768, 512, 1, op, 0, ctypes.byref(n)) == 0 and n.value > 0

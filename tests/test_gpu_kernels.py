@@ -644,3 +644,22 @@ def test_small_pack_concatenates_and_casts():
     b = torch.randn(64, 512, device="cuda")
     out = be.small_pack(a, b, torch.bfloat16)
     assert out.shape == (2, 64, 512) and torch.equal(out[0], a.bfloat16()) and torch.equal(out[1], b.bfloat16())
+
+
+def test_unnormalised_bf16_features_inside_the_f16_range_keep_exact_gradients():
+    """the bf16 backward multiplies G with an f16 copy of the features.  Inside the f16 range (here rows of norm
+    ~40, elements up to ~6) nothing is lost; the documented limit is |v| <= 65504 (loss.py / INTEGRATION.md)."""
+    from mamba_clip_b200 import ClipLoss
+    B, D, ls = 2048, 256, 0.01            # un-normalised rows: keep the logits moderate through a small scale
+    g = torch.Generator().manual_seed(3)
+    img = (torch.randn(B, D, generator=g) * 2.5).bfloat16()
+    txt = (img.float() + 0.5 * torch.randn(B, D, generator=g)).bfloat16()
+    ref = O.closed_form(img.float(), txt.float(), ls, 1, 0, False, False, grad_output=1.0)
+    a = img.cuda().requires_grad_(True)
+    b = txt.cuda().requires_grad_(True)
+    s = torch.tensor(ls, device="cuda", requires_grad=True)
+    loss = ClipLoss()(a, b, s, output_dict=False)
+    loss.backward()
+    assert abs(float(loss.detach()) - float(ref.loss)) <= 2e-3 * abs(float(ref.loss)) + 1e-6
+    assert O.rel_err(a.grad.cpu(), ref.d_image) <= 2e-3 and O.rel_err(b.grad.cpu(), ref.d_text) <= 2e-3
+    assert abs(float(s.grad) - float(ref.d_logit_scale)) <= 2e-3 * abs(float(ref.d_logit_scale))
