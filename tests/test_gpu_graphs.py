@@ -72,3 +72,24 @@ def test_graph_buffers_released_when_loss_is_dropped_and_eager_fallback_when_pen
     with torch.no_grad():
         l4 = crit(img.cuda(), txt.cuda(), torch.tensor(20.0, device="cuda"), output_dict=False)
     assert abs(float(l4) - float(ref.loss)) <= 2e-3 * abs(float(ref.loss))
+
+
+def test_graph_replay_of_the_shared_recompute_backward(graphs):
+    """B = 8192 is below the graph work limit AND large enough for mclip_fused_grad: its fork/join onto the library's
+    side stream (events) must capture into the backward graph and replay bit-identically."""
+    import mamba_clip_b200 as M
+    from mamba_clip_b200 import ClipLoss, _cabi
+    B, D = 8192, 512
+    crit = ClipLoss()
+    assert _cabi.get_backend().fused_supported(torch.empty(B, D, dtype=torch.bfloat16, device="cuda"),
+                                               torch.empty(B, D, dtype=torch.bfloat16, device="cuda"))
+    data = [O.make_features(B, D, seed=300 + k, dtype=torch.bfloat16) + (14.2857 + k, 1.0 + k) for k in range(5)]
+    M.enable_cuda_graphs(False)
+    eager = [_step(crit, i, t, ls, go) for i, t, ls, go in data]
+    M.enable_cuda_graphs(True)
+    graphed = [_step(crit, i, t, ls, go) for i, t, ls, go in data]
+    key = [k for k in graphs._graph_cache if k[1] == (B, D)]
+    assert len(key) == 1 and len(graphs._graph_cache[key[0]].graphs) >= 2
+    for (l0, di0, dt0, ds0), (l1, di1, dt1, ds1) in zip(eager, graphed):
+        assert l0 == l1 and ds0 == ds1
+        assert torch.equal(di0, di1) and torch.equal(dt0, dt1)
