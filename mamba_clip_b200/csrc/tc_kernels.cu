@@ -2772,7 +2772,7 @@ FusedWs fused_ws_layout(const FusedPlan& f, int64_t M, int64_t N, int64_t D, boo
   w.y16 = off;   off += bf ? align_up((size_t)N * D * 2, 256) : 0;
   w.x16 = off;   off += bf ? align_up((size_t)M * D * 2, 256) : 0;
   w.acc_y = off; off += align_up((size_t)N * D * sizeof(float), 256);
-  w.acc_x = off; off += align_up((size_t)f.b.nsplit * f.panel_rows * D * sizeof(float), 256);
+  w.acc_x = off; off += 2 * align_up((size_t)f.b.nsplit * f.panel_rows * D * sizeof(float), 256);   // double-buffered
   w.g = off;     off += 2 * align_up((size_t)f.panel_rows * f.n_pad * 2, 1024);
   w.total = off;
   return w;
@@ -2845,32 +2845,38 @@ int fused_grad_impl(const FusedGradArgs& a) {
   g.logit_scale = a.logit_scale; g.grad_out = a.grad_out; g.lse_x = a.lse_x; g.lse_y = a.lse_y; g.diag_off = a.diag_off;
   g.w_row = 1.f; g.w_col = 1.f; g.w_diag = 2.f; g.inv_2n = a.inv_2n; g.dX = a.dX; g.lddx = a.lddx; g.rowdot = nullptr;
   g.ws = nullptr; g.ws_bytes = 0; g.stream = a.stream;
-  Bwd2Prep pr;
-  int rc = bwd2_prepare(g, f.n_pad, reinterpret_cast<float*>(ws + w.stat), ws + w.y16, &pr);
+  FusedStreams* fs = nullptr;
+  int rc = fused_streams(2 * f.panels + 2, &fs);
   if (rc) return rc;
+  // fork: everything only the dY product needs (the f16 copy of X, the partial sums of each panel, the GEMM itself) runs on
+  // the side stream, so that the main stream is nothing but prep + back-to-back recompute launches
+  cudaEvent_t ev_fork = fs->ev[2 * f.panels];
+  MCLIP_CUDA_OK(cudaEventRecord(ev_fork, a.stream));
+  MCLIP_CUDA_OK(cudaStreamWaitEvent(fs->side, ev_fork, 0));
   const void* x16 = a.X;
   int64_t ldx16 = a.ldx;
   if (bf) {
     __half* dst = reinterpret_cast<__half*>(ws + w.x16);
     const int64_t n8 = a.M * (a.D / 8);
-    bf16_to_f16_kernel<<<ew_blocks(n8, 256), 256, 0, a.stream>>>(reinterpret_cast<const __nv_bfloat16*>(a.X), a.M, a.D, a.ldx, dst);
+    bf16_to_f16_kernel<<<ew_blocks(n8, 256), 256, 0, fs->side>>>(reinterpret_cast<const __nv_bfloat16*>(a.X), a.M, a.D, a.ldx, dst);
     count_launch();
     MCLIP_CUDA_OK(cudaGetLastError());
     x16 = dst;
     ldx16 = a.D;
   }
-  float* acc_y = reinterpret_cast<float*>(ws + w.acc_y);
-  float* acc_x = reinterpret_cast<float*>(ws + w.acc_x);
-  const size_t g_stride = align_up((size_t)f.panel_rows * f.n_pad * 2, 1024);
-  FusedStreams* fs = nullptr;
-  rc = fused_streams(2 * f.panels + 1, &fs);
+  Bwd2Prep pr;
+  rc = bwd2_prepare(g, f.n_pad, reinterpret_cast<float*>(ws + w.stat), ws + w.y16, &pr);
   if (rc) return rc;
+  float* acc_y = reinterpret_cast<float*>(ws + w.acc_y);
+  const size_t accx_stride = align_up((size_t)f.b.nsplit * f.panel_rows * a.D * sizeof(float), 256);
+  const size_t g_stride = align_up((size_t)f.panel_rows * f.n_pad * 2, 1024);
   const int slots = pair_slots();
   for (int pi = 0; pi < f.panels; ++pi) {
     const int64_t r0 = (int64_t)pi * f.panel_rows;
     const int64_t rows = (a.M - r0 < f.panel_rows) ? a.M - r0 : f.panel_rows;
     void* gbuf = ws + w.g + (size_t)(pi & 1) * g_stride;
-    if (pi >= 2) MCLIP_CUDA_OK(cudaStreamWaitEvent(a.stream, fs->ev[2 * (pi - 2) + 1], 0));   // G buffer free again
+    float* acc_x = reinterpret_cast<float*>(ws + w.acc_x + (size_t)(pi & 1) * accx_stride);
+    if (pi >= 2) MCLIP_CUDA_OK(cudaStreamWaitEvent(a.stream, fs->ev[2 * (pi - 2) + 1], 0));   // G and partial buffers free again
     BlockGradArgs gp = g;
     gp.X = reinterpret_cast<const T*>(a.X) + r0 * a.ldx;
     gp.M = rows;
@@ -2879,13 +2885,13 @@ int fused_grad_impl(const FusedGradArgs& a) {
     gp.dX = reinterpret_cast<T*>(a.dX) + r0 * a.lddx;
     rc = bwd2_launch(gp, f.b, pr, acc_x, nullptr, gbuf, f.n_pad, true);
     if (rc) return rc;
-    acc_to_dx_dot_kernel<T><<<ew_blocks(rows * 32, 256), 256, 0, a.stream>>>(
+    MCLIP_CUDA_OK(cudaEventRecord(fs->ev[2 * pi], a.stream));
+    MCLIP_CUDA_OK(cudaStreamWaitEvent(fs->side, fs->ev[2 * pi], 0));
+    acc_to_dx_dot_kernel<T><<<ew_blocks(rows * 32, 256), 256, 0, fs->side>>>(
         acc_x, f.b.nsplit, rows, a.D, reinterpret_cast<const T*>(gp.X), a.ldx, a.logit_scale, a.grad_out,
         a.inv_2n * (1.f / kGScale), reinterpret_cast<T*>(gp.dX), a.lddx, a.xdot + r0);
     count_launch();
     MCLIP_CUDA_OK(cudaGetLastError());
-    MCLIP_CUDA_OK(cudaEventRecord(fs->ev[2 * pi], a.stream));
-    MCLIP_CUDA_OK(cudaStreamWaitEvent(fs->side, fs->ev[2 * pi], 0));
     rc = launch_gemm_tn(gbuf, f.n_pad / 64, reinterpret_cast<const __half*>(x16) + r0 * ldx16, ldx16, acc_y, a.D, rows, a.N, a.D,
                         slots, options().dbg, pi == 0, fs->side);
     if (rc) return rc;
