@@ -191,10 +191,9 @@ def _forward_impl(be, xi, xt, ls, local_loss, gather_with_grad, rank, W, group, 
             work_t = _gather_into(all_t, xt.clone() if gathered is not None else xt, group, None)
             work_i = _gather_into(all_i, xi.clone() if gathered is not None else xi, group, None)
         off = int(rank) * Bl
-        work_t.wait()
     else:
         all_i, all_t, off = xi, xt, 0
-        work_i = None
+        work_i = work_t = None
 
     # u, v: softmax-weighted raw dots (sum_j P_ij <x_i, y_j>) of the two blocks -- all d(logit_scale) needs
     row_lse_all = col_lse_all = None      # full-length LSE vectors, when the forward already leaves them on every rank
@@ -218,14 +217,17 @@ def _forward_impl(be, xi, xt, ls, local_loss, gather_with_grad, rank, W, group, 
             # all-gather every rank holds everything: it finishes ALL columns itself and has every rank's row LSEs, so
             # backward needs no further exchange.  The status words are ORed on every rank alike; if any is set, every
             # rank redoes the full row and column statistics with the robust one-sided kernels (W x redundant, rare).
+            # the positive pairs of the rank's rows are its own text rows: the exponent reference does not need the gather
+            diag, ref, status = run.seg("fwd_ref", lambda: be.pair_ref(xi, xt, ls, 0))
+            work_t.wait()
+
             def seg_a():
-                diag, ref, status = be.pair_ref(xi, all_t, ls, off)
                 msg = torch.empty(Bg + 2 + Bl, dtype=torch.float32, device=dev)
                 u_all = torch.empty(Bg, dtype=torch.float32, device=dev) if need_ls else None   # only [off, off + B_l) is read
                 be.pair_lse(xi, all_t, ls, ref, status, need_ls, col_mode=1, diag=diag, diag_off=off, out_msg=msg,
                             out_rowdot=u_all[off:off + Bl] if need_ls else None)
-                return diag, status, msg, u_all
-            diag, status, msg, u_all = run.seg("fwd_a", seg_a)
+                return msg, u_all
+            msg, u_all = run.seg("fwd_a", seg_a)
             parts = run.buffer("col_parts", (W, Bg + 2 + Bl), torch.float32, dev)
             _gather_into(parts, msg.unsqueeze(0), group, comm).wait()
             work_i.wait()
@@ -241,6 +243,8 @@ def _forward_impl(be, xi, xt, ls, local_loss, gather_with_grad, rank, W, group, 
             u = u_all[off:off + Bl] if need_ls else None
         uv = (u, None) if need_ls else None   # v comes out of the text-side backward kernel
     else:
+        if work_t is not None:
+            work_t.wait()
         if work_i is not None:
             work_i.wait()
 
