@@ -104,8 +104,10 @@ __device__ __forceinline__ float block_sum_256(float v, float* red) {
 template <typename T>
 __global__ void __launch_bounds__(256)
 small_fwd_kernel(const SmallFwdParams p) {
-  __shared__ float Xs[kBK][kT + 1];
-  __shared__ float Ys[kBK][kT + 1];
+  // k-major tiles with a 16-byte aligned pitch: a thread's 4 rows / 4 columns at one k are ONE ld.shared.v4, and the 16
+  // lanes that share rows read the same address (broadcast): ~3 shared-memory wavefronts per k and warp instead of 8+
+  __shared__ __align__(16) float Xs[kBK][kT + 4];
+  __shared__ __align__(16) float Ys[kBK][kT + 4];
   __shared__ float red[8];
   __shared__ unsigned flag;
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
@@ -128,21 +130,24 @@ small_fwd_kernel(const SmallFwdParams p) {
   const bool xr_ok = row0 + sr < p.Bg, yr_ok = col0 + sr < p.Bg;
   const T* xrow = row_ptr<T>(X, xr_ok ? row0 + sr : 0, p.Bl, p.blk_stride, p.D);
   const T* yrow = row_ptr<T>(Y, yr_ok ? col0 + sr : 0, p.Bl, p.blk_stride, p.D);
-  for (int k0 = 0; k0 < p.D; k0 += kBK) {
-    float xv[8], yv[8];
+  // register prefetch: the global loads of chunk k0 + 32 are in flight while chunk k0 is multiplied
+  float xv[8], yv[8];
+  auto fetch = [&](int k0) {
     const int gk = k0 + skq * 8;
     if (xr_ok && gk < p.D) load8<T>(xrow + gk, xv); else { for (int e = 0; e < 8; ++e) xv[e] = 0.f; }
     if (yr_ok && gk < p.D) load8<T>(yrow + gk, yv); else { for (int e = 0; e < 8; ++e) yv[e] = 0.f; }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < p.D; k0 += kBK) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) { Xs[skq * 8 + e][sr] = xv[e]; Ys[skq * 8 + e][sr] = yv[e]; }
     __syncthreads();
+    if (k0 + kBK < p.D) fetch(k0 + kBK);
 #pragma unroll
     for (int k = 0; k < kBK; ++k) {
-      float xa[4], yb[4];
-#pragma unroll
-      for (int a = 0; a < 4; ++a) xa[a] = Xs[k][ty * 4 + a];
-#pragma unroll
-      for (int b = 0; b < 4; ++b) yb[b] = Ys[k][tx * 4 + b];
+      const float4 xq = *reinterpret_cast<const float4*>(&Xs[k][ty * 4]);
+      const float4 yq = *reinterpret_cast<const float4*>(&Ys[k][tx * 4]);
+      const float xa[4] = {xq.x, xq.y, xq.z, xq.w}, yb[4] = {yq.x, yq.y, yq.z, yq.w};
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -256,6 +261,7 @@ small_bwd_kernel(const SmallBwdParams p) {
     p.dls_out[0] = (p.go ? p.go[0] : 1.f) * p.dls_scale * p.stats[5 * p.Bg + 1];
 
   // stage the CTA's X rows as f32
+#pragma unroll 4
   for (int idx = tid; idx < kBR * d8; idx += 256) {
     const int r = idx / d8, k = (idx - r * d8) * 8;
     float v[8];
@@ -277,6 +283,7 @@ small_bwd_kernel(const SmallBwdParams p) {
 
   for (int c0 = c_begin; c0 < c_end; c0 += kBC) {
     __syncthreads();                              // previous chunk's Ys / Gs fully consumed (and Xs staged)
+#pragma unroll 4
     for (int idx = tid; idx < kBC * d8; idx += 256) {
       const int r = idx / d8, k = (idx - r * d8) * 8;
       float v[8];
