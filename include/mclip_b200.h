@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MCLIP_ABI_VERSION 5
+#define MCLIP_ABI_VERSION 6
 
 enum { MCLIP_DTYPE_F32 = 0, MCLIP_DTYPE_BF16 = 1, MCLIP_DTYPE_F16 = 2 };
 enum { MCLIP_PATH_AUTO = 0, MCLIP_PATH_SIMT = 1, MCLIP_PATH_TCGEN05 = 2 };
@@ -124,12 +124,19 @@ int mclip_lse_from_sum(const float* sum, int64_t n, const float* ref, float* lse
  * NllLossBackward) for one side.  `lse_y` may be NULL iff w_col == 0 (local_loss without
  * gather_with_grad: own-row terms only).  `grad_out` is a device scalar (GradScaler's scale reaches
  * the loss through it, reference train.py:59-63) or NULL for 1.  `rowdot` may be NULL.
+ * `Y16` (may be NULL; only read for bf16 inputs on the tcgen05 path): an f16 copy of Y, [N, D] contiguous, made ahead of
+ * time with mclip_convert_f16 -- e.g. on a side stream next to the forward kernel -- so that the call does not spend its
+ * own pass over Y on it (G is f16 * 2^12 and the dX MMA needs both operands in f16).
  */
 int mclip_block_grad(const void* X, const void* Y, int64_t M, int64_t N, int64_t D, int64_t ldx, int64_t ldy,
                      int dtype, const float* logit_scale, const float* grad_out, const float* lse_x,
                      const float* lse_y, int64_t diag_off, float w_row, float w_col, float w_diag,
-                     float inv_2n, void* dX, int64_t lddx, float* rowdot, void* ws, size_t ws_bytes,
+                     float inv_2n, void* dX, int64_t lddx, float* rowdot, const void* Y16, void* ws, size_t ws_bytes,
                      int path, void* cuda_stream);
+
+/* dst[rows, D] (f16, contiguous) = src[rows, D] (bf16, leading dimension ld): exact for 6.1e-5 <= |v| <= 65504, saturating
+ * above.  D % 8 == 0, 16-byte aligned pointers. */
+int mclip_convert_f16(const void* src, int64_t rows, int64_t D, int64_t ld, void* dst, void* cuda_stream);
 
 /*
  * Both feature gradients of one logits block from ONE recompute of it (the backward of reference loss.py:102-111,

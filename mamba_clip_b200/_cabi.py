@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # MCLIP_LIB_PATH: development only (e.g. a -DMCLIP_PROFILE build next to the release library)
 LIB_PATH = os.environ.get("MCLIP_LIB_PATH") or os.path.join(_HERE, "libmclip_b200.so")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 DTYPE_CODES = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
 PATH_AUTO, PATH_SIMT, PATH_TCGEN05 = 0, 1, 2
 OP_ROW_LSE, OP_BLOCK_GRAD, OP_PAIR_LSE, OP_PAIR_REF, OP_FUSED_GRAD, OP_SMALL = 0, 1, 2, 3, 4, 5
@@ -44,8 +44,10 @@ _SIGNATURES = {
     "mclip_lse_from_sum": (ctypes.c_int, [_c_f32p, ctypes.c_int64, _c_f32p, _c_f32p, ctypes.c_void_p, ctypes.c_void_p]),
     "mclip_block_grad": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int64] * 5 + [ctypes.c_int, _c_f32p,
                                         _c_f32p, _c_f32p, _c_f32p, ctypes.c_int64] + [ctypes.c_float] * 4 +
-                         [ctypes.c_void_p, ctypes.c_int64, _c_f32p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
+                         [ctypes.c_void_p, ctypes.c_int64, _c_f32p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
                           ctypes.c_void_p]),
+    "mclip_convert_f16": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
+                                         ctypes.c_void_p]),
     "mclip_fused_grad_supported": (ctypes.c_int, [ctypes.c_int64] * 5 + [ctypes.c_int]),
     "mclip_fused_grad": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int64] * 5 + [ctypes.c_int, _c_f32p,
                                         _c_f32p, _c_f32p, _c_f32p, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p,
@@ -286,7 +288,19 @@ class CudaBackend:
         _check(self.lib, rc, "mclip_lse_from_sum")
         return lse
 
-    def block_grad(self, X, Y, ls, go, lse_x, lse_y, diag_off, w_row, w_col, w_diag, inv_2n, want_rowdot=True):
+    def to_f16(self, src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """f16 copy of a bf16 matrix (mclip_convert_f16) on the current stream; `out`: a [rows, D] contiguous f16 buffer."""
+        dev = self._prep(src)
+        rows, D = src.shape
+        if out is None:
+            out = torch.empty((rows, D), dtype=torch.float16, device=dev)
+        with self._DeviceGuard(dev):
+            rc = self.lib.mclip_convert_f16(_ptr(src), rows, D, src.stride(0), _ptr(out),
+                                            ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        _check(self.lib, rc, "mclip_convert_f16")
+        return out
+
+    def block_grad(self, X, Y, ls, go, lse_x, lse_y, diag_off, w_row, w_col, w_diag, inv_2n, want_rowdot=True, y16=None):
         dev = self._prep(X, Y, ls, lse_x)
         M, D = X.shape
         N = Y.shape[0]
@@ -297,7 +311,7 @@ class CudaBackend:
         with self._DeviceGuard(dev):
             rc = self.lib.mclip_block_grad(_ptr(X), _ptr(Y), M, N, D, X.stride(0), Y.stride(0), DTYPE_CODES[X.dtype],
                                            _ptr(ls), _ptr(go), _ptr(lse_x), _ptr(lse_y), diag_off, w_row, w_col,
-                                           w_diag, inv_2n, _ptr(dX), dX.stride(0), _ptr(rowdot), _ptr(ws), nws,
+                                           w_diag, inv_2n, _ptr(dX), dX.stride(0), _ptr(rowdot), _ptr(y16), _ptr(ws), nws,
                                            self.path, ctypes.c_void_p(stream))
         _check(self.lib, rc, "mclip_block_grad")
         return dX, rowdot

@@ -110,6 +110,34 @@ def _on_comm_stream(dev, fn):
     return _EventWait(ev)
 
 
+_prep_streams = {}
+
+
+def _start_f16_copies(be, run, all_i, all_t, work_i, work_t):
+    """bf16 inputs: the backward's dX MMA needs an f16 copy of each `[N, D]` operand (G is f16 * 2^12).  Make both copies
+    on a per-device side stream as soon as the (gathered) features exist -- next to the forward kernel, which is tensor
+    bound and leaves the memory system idle -- instead of in front of each recompute launch.  -> (y16_i, y16_t, event)."""
+    dev = all_t.device
+    ps = _prep_streams.get(dev.index)
+    if ps is None:
+        ps = _prep_streams[dev.index] = torch.cuda.Stream(device=dev)
+    ps.wait_stream(torch.cuda.current_stream(dev))
+    y16_t = run.buffer("y16_t", tuple(all_t.shape), torch.float16, dev)
+    y16_i = run.buffer("y16_i", tuple(all_i.shape), torch.float16, dev)
+    y16_t.record_stream(ps)       # allocated on the compute stream, written on the side stream
+    y16_i.record_stream(ps)
+    with torch.cuda.stream(ps):
+        if work_t is not None:
+            work_t.wait()
+        be.to_f16(all_t, out=y16_t)
+        if work_i is not None:
+            work_i.wait()
+        be.to_f16(all_i, out=y16_i)
+        ev = torch.cuda.Event()
+        ev.record(ps)
+    return y16_i, y16_t, ev
+
+
 def _gather_into(out, x, group, comm=None):
     """All-gather into a caller-provided buffer: directly through NCCL on the current stream when a direct
     communicator exists (see _nccl.py), else through torch.distributed.  Returns a handle with `.wait()`."""
@@ -162,7 +190,7 @@ def _small_backward_impl(be, st, go, local_loss, gather_with_grad, W, need_ls, r
 
 
 def _forward_impl(be, xi, xt, ls, local_loss, gather_with_grad, rank, W, group, need_ls, run=_EAGER, gathered=None,
-                  allow_small=False):
+                  allow_small=False, for_backward=False):
     if allow_small and gathered is None:      # the caller has already asked be.small_supported(...)
         return _small_forward_impl(be, xi, xt, ls, local_loss, rank, W, group, run)
     """Everything `ClipLoss.forward` launches, on already-cast contiguous inputs.  Returns the state dict that
@@ -194,6 +222,15 @@ def _forward_impl(be, xi, xt, ls, local_loss, gather_with_grad, rank, W, group, 
     else:
         all_i, all_t, off = xi, xt, 0
         work_i = work_t = None
+
+    f16_copies = None
+    if (for_backward and xi.dtype == torch.bfloat16 and dev.type == "cuda" and hasattr(be, "to_f16") and xi.shape[1] % 8 == 0 and xi.shape[1] <= 768
+            and not torch.cuda.is_current_stream_capturing()
+            and not (W == 1 and getattr(be, "fused_supported", lambda *_: False)(xi, all_t))):
+        # (c10d handles -- the fallback collectives -- are waited for on the compute stream only)
+        f16_copies = _start_f16_copies(be, run, all_i, all_t, work_i if isinstance(work_i, _EventWait) else None,
+                                       work_t if isinstance(work_t, _EventWait) else None) \
+            if (W == 1 or isinstance(work_t, _EventWait)) else None
 
     # u, v: softmax-weighted raw dots (sum_j P_ij <x_i, y_j>) of the two blocks -- all d(logit_scale) needs
     row_lse_all = col_lse_all = None      # full-length LSE vectors, when the forward already leaves them on every rank
@@ -269,7 +306,7 @@ def _forward_impl(be, xi, xt, ls, local_loss, gather_with_grad, rank, W, group, 
         stats_work = _gather_into(stats, torch.stack((row_lse, col_lse)).unsqueeze(0), group, comm)
     return dict(loss=loss, xi=xi, xt=xt, all_i=all_i, all_t=all_t, ls=ls, row_lse=row_lse, col_lse=col_lse, diag=diag,
                 uv=uv, stats=stats, stats_work=stats_work, off=off, own_terms_only=own_terms_only,
-                row_lse_all=row_lse_all, col_lse_all=col_lse_all)
+                row_lse_all=row_lse_all, col_lse_all=col_lse_all, f16_copies=f16_copies)
 
 
 def _backward_impl(be, st, go, local_loss, gather_with_grad, W, group, need_i, need_t, need_ls, run=_EAGER, rows=None):
@@ -288,6 +325,10 @@ def _backward_impl(be, st, go, local_loss, gather_with_grad, W, group, need_i, n
     stats = st["stats"]
     Bl = xi.shape[0]
     Bg = W * Bl
+    y16_i = y16_t = None
+    if st.get("f16_copies") is not None:
+        y16_i, y16_t, ev16 = st["f16_copies"]
+        torch.cuda.current_stream(xi.device).wait_event(ev16)
 
     # 1/(2n) of the feature gradients: the true gradient for W=1 and (False, False),
     # W x that otherwise.
@@ -314,6 +355,8 @@ def _backward_impl(be, st, go, local_loss, gather_with_grad, W, group, need_i, n
             w_row, w_col, w_diag = 1.0, 1.0, 2.0
             lse_y_i, lse_y_t = col_lse_all, row_lse_all
         d_img = d_txt = t = d_ls = v_bwd = None
+        kw_t = {"y16": y16_t} if y16_t is not None else {}      # f16 copies made next to the forward kernel
+        kw_i = {"y16": y16_i} if y16_i is not None else {}
         if (W == 1 and rows is None and need_i and need_t and not own_terms_only
                 and getattr(be, "fused_supported", lambda *_: False)(xi, all_t)):
             # shared-recompute backward: one recompute of S feeds dI = G T and dT = G^T I (4 GEMM units per step
@@ -326,17 +369,17 @@ def _backward_impl(be, st, go, local_loss, gather_with_grad, W, group, need_i, n
             lo, hi = rows
             if need_i:
                 d_img, _ = be.block_grad(xi[lo:hi], all_t, ls, go, row_lse[lo:hi], lse_y_i, off + lo, w_row, w_col, w_diag,
-                                         inv_2n, False)
+                                         inv_2n, False, **kw_t)
             if need_t:
                 d_txt, _ = be.block_grad(xt[lo:hi], all_i, ls, go, col_lse[lo:hi], lse_y_t, off + lo, w_row, w_col, w_diag,
-                                         inv_2n, False)
+                                         inv_2n, False, **kw_i)
             if want_v:      # v of ALL local rows feeds d(logit_scale): one forward-only pass of the text side
                 v_bwd = be.row_lse(xt, all_i, ls, off, False, True)[2]
         else:
             if need_i:
-                d_img, _ = be.block_grad(xi, all_t, ls, go, row_lse, lse_y_i, off, w_row, w_col, w_diag, inv_2n, False)
+                d_img, _ = be.block_grad(xi, all_t, ls, go, row_lse, lse_y_i, off, w_row, w_col, w_diag, inv_2n, False, **kw_t)
             if need_t:
-                d_txt, v_bwd = be.block_grad(xt, all_i, ls, go, col_lse, lse_y_t, off, w_row, w_col, w_diag, inv_2n, want_v)
+                d_txt, v_bwd = be.block_grad(xt, all_i, ls, go, col_lse, lse_y_t, off, w_row, w_col, w_diag, inv_2n, want_v, **kw_i)
             elif want_v:
                 v_bwd = be.row_lse(xt, all_i, ls, off, False, True)[2]
         if need_ls:
@@ -457,7 +500,8 @@ class _GraphedLoss:
             g, self.state = self.graphs["fwd"]
             g.replay()
         else:
-            self.state = _forward_impl(be, self.xi, self.xt, self.ls, local_loss, gwg, rank, W, group, self.need_ls, run=self)
+            self.state = _forward_impl(be, self.xi, self.xt, self.ls, local_loss, gwg, rank, W, group, self.need_ls, run=self,
+                                       for_backward=True)
         self.generation += 1
         return self.state["loss"].clone()
 
@@ -522,7 +566,8 @@ class ClipLossFunction(torch.autograd.Function):
                 ctx.ls_meta = (logit_scale.dtype, logit_scale.shape, logit_scale.device) if torch.is_tensor(logit_scale) else None
                 return loss
 
-        st = _forward_impl(be, xi, xt, ls, bool(local_loss), bool(gather_with_grad), int(rank), W, group, need_ls, allow_small=small)
+        st = _forward_impl(be, xi, xt, ls, bool(local_loss), bool(gather_with_grad), int(rank), W, group, need_ls, allow_small=small,
+                           for_backward=wants_grad)
         loss = st.pop("loss")
         if not st.get("small"):
             # tensors go through save_for_backward (in-place modification checks); `stats` is written by an in-flight

@@ -159,7 +159,8 @@ int mclip_lse_from_sum(const float* sum, int64_t n, const float* ref, float* lse
 int mclip_block_grad(const void* X, const void* Y, int64_t M, int64_t N, int64_t D, int64_t ldx, int64_t ldy,
                      int dtype, const float* logit_scale, const float* grad_out, const float* lse_x,
                      const float* lse_y, int64_t diag_off, float w_row, float w_col, float w_diag, float inv_2n,
-                     void* dX, int64_t lddx, float* rowdot, void* ws, size_t ws_bytes, int path, void* cuda_stream) {
+                     void* dX, int64_t lddx, float* rowdot, const void* Y16, void* ws, size_t ws_bytes, int path,
+                     void* cuda_stream) {
   int rc = check_common(X, Y, M, N, D, ldx, ldy, dtype, logit_scale, path, "block_grad");
   if (rc) return rc;
   if (!lse_x || !dX) { set_error("block_grad: null lse_x/dX"); return MCLIP_ERR_INVALID; }
@@ -171,8 +172,10 @@ int mclip_block_grad(const void* X, const void* Y, int64_t M, int64_t N, int64_t
   if (rc) return rc;
   const size_t need = (p == MCLIP_PATH_TCGEN05) ? tc_block_grad_ws(M, N, D) : simt_block_grad_ws(M, N, D);
   if (need > 0 && (!ws || ws_bytes < need)) { set_error("block_grad: workspace %zu < %zu bytes", ws_bytes, need); return MCLIP_ERR_WORKSPACE; }
+  if (Y16 && (((uintptr_t)Y16) & 15)) { set_error("block_grad: Y16 must be 16-byte aligned"); return MCLIP_ERR_INVALID; }
   BlockGradArgs a{X, Y, M, N, D, ldx, ldy, dtype, logit_scale, grad_out, lse_x, lse_y, diag_off,
                   w_row, w_col, w_diag, inv_2n, dX, lddx, rowdot, ws, ws_bytes, (cudaStream_t)cuda_stream};
+  a.y16 = (dtype == MCLIP_DTYPE_BF16) ? Y16 : nullptr;
   return (p == MCLIP_PATH_TCGEN05) ? tc_block_grad(a) : simt_block_grad(a);
 }
 
@@ -252,6 +255,14 @@ int mclip_small_backward(const void* A, const void* B, int64_t Bl, int64_t Bg, i
 int mclip_small_pack(const void* a, const void* b, int64_t n, int in_dtype, int out_dtype, void* out, void* cuda_stream) {
   if (!a || !b || !out || n <= 0 || !valid_dtype(in_dtype) || !valid_dtype(out_dtype)) { set_error("small_pack: invalid argument"); return MCLIP_ERR_INVALID; }
   return small_pack(a, b, n, in_dtype, out_dtype, out, (cudaStream_t)cuda_stream);
+}
+
+int mclip_convert_f16(const void* src, int64_t rows, int64_t D, int64_t ld, void* dst, void* cuda_stream) {
+  if (!src || !dst || rows <= 0 || D <= 0 || D % 8 != 0 || ld < D || ld % 8 != 0 || ((((uintptr_t)src) | ((uintptr_t)dst)) & 15)) {
+    set_error("convert_f16: needs 16-byte aligned pointers, D %% 8 == 0, ld %% 8 == 0");
+    return MCLIP_ERR_INVALID;
+  }
+  return launch_convert_f16(src, rows, D, ld, dst, (cudaStream_t)cuda_stream);
 }
 
 int mclip_set_option(const char* name, int value) { return tc_set_option(name, value); }

@@ -88,6 +88,7 @@ struct BlockGradArgs {
   float* rowdot;          // may be null
   void* ws; size_t ws_bytes;
   cudaStream_t stream;
+  const void* y16 = nullptr;   // optional f16 copy of Y ([N, D] contiguous) made ahead of time: bf16 inputs skip their own conversion
 };
 
 // shared-recompute backward: both feature gradients from ONE recompute of the logits block (tc_kernels.cu)
@@ -147,6 +148,7 @@ int tc_block_grad(const BlockGradArgs& a);
 bool tc_fused_supported(int64_t M, int64_t N, int64_t D, int64_t ldx, int64_t ldy, int dtype);
 size_t tc_fused_grad_ws(int64_t M, int64_t N, int64_t D);
 int tc_fused_grad(const FusedGradArgs& a);
+int launch_convert_f16(const void* src, int64_t rows, int64_t D, int64_t ld, void* dst, cudaStream_t stream);
 int tc_set_option(const char* name, int value);
 int tc_get_option(const char* name, int* value);
 

@@ -2546,7 +2546,10 @@ int tc_block_grad2p(const BlockGradArgs& a) {
   }
   const void* y16 = a.Y;
   int64_t ld16 = a.ldy;
-  if (bf) {
+  if (bf && a.y16 != nullptr) {
+    y16 = a.y16;
+    ld16 = a.D;
+  } else if (bf) {
     __half* dst = reinterpret_cast<__half*>(ws + w.y16);
     const int64_t n8 = a.N * (a.D / 8);
     const unsigned blocks = ew_blocks(n8, 256);
@@ -2627,7 +2630,10 @@ int bwd2_prepare(const BlockGradArgs& a, int64_t n_pad, float* stat_ws, void* y1
   }
   r.y16 = a.Y;
   r.ld16 = a.ldy;
-  if (a.dtype == MCLIP_DTYPE_BF16) {
+  if (a.dtype == MCLIP_DTYPE_BF16 && a.y16 != nullptr) {        // converted ahead of time by the caller (mclip_convert_f16)
+    r.y16 = a.y16;
+    r.ld16 = a.D;
+  } else if (a.dtype == MCLIP_DTYPE_BF16) {
     __half* dst = reinterpret_cast<__half*>(y16_ws);
     const int64_t n8 = a.N * (a.D / 8);
     bf16_to_f16_kernel<<<ew_blocks(n8, 256), 256, 0, a.stream>>>(reinterpret_cast<const __nv_bfloat16*>(a.Y), a.N, a.D, a.ldy, dst);
@@ -2911,6 +2917,15 @@ int fused_grad_impl(const FusedGradArgs& a) {
 
 }  // namespace
 
+int launch_convert_f16(const void* src, int64_t rows, int64_t D, int64_t ld, void* dst, cudaStream_t stream) {
+  const int64_t n8 = rows * (D / 8);
+  bf16_to_f16_kernel<<<ew_blocks(n8, 256), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(src), rows, D, ld,
+                                                             reinterpret_cast<__half*>(dst));
+  count_launch();
+  MCLIP_CUDA_OK(cudaGetLastError());
+  return MCLIP_OK;
+}
+
 bool tc_fused_supported(int64_t M, int64_t N, int64_t D, int64_t ldx, int64_t ldy, int dtype) {
   if (!options().fused_bwd) return false;
   if (!tc_supported(M, N, D, ldx, ldy, dtype, MCLIP_OP_BLOCK_GRAD) || D > 512) return false;
@@ -2940,7 +2955,10 @@ int tc_block_grad(const BlockGradArgs& a) {
   const void* y16 = a.Y;
   int64_t ld16 = a.ldy;
   int rc;
-  if (bf) {
+  if (bf && a.y16 != nullptr) {
+    y16 = a.y16;
+    ld16 = a.D;
+  } else if (bf) {
     __half* dst = reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(a.ws) + acc_bytes);
     const int64_t n8 = a.N * (a.D / 8);
     const unsigned blocks = ew_blocks(n8, 256);

@@ -50,8 +50,9 @@ def test_argument_validation_without_gpu(lib):
     rc = lib.mclip_row_lse(None, None, 4, 4, 8, 8, 8, 0, None, 0, None, None, None, None, None, 0, 0, None)
     assert rc == 1 and b"null" in lib.mclip_last_error()
     rc = lib.mclip_block_grad(None, None, 4, 4, 8, 8, 8, 0, None, None, None, None, 0, 1.0, 1.0, 2.0, 0.5,
-                              None, 8, None, None, 0, 0, None)
+                              None, 8, None, None, None, 0, 0, None)
     assert rc == 1
+    assert lib.mclip_convert_f16(None, 4, 8, 8, None, None) == 1
     assert lib.mclip_loss_finalize(None, None, None, 4, None, None, None) == 1
     assert lib.mclip_dls_finalize(None, None, None, 4, None, 1.0, None, None, None) == 1
     # two-sided forward entry points

@@ -663,3 +663,20 @@ def test_unnormalised_bf16_features_inside_the_f16_range_keep_exact_gradients():
     assert abs(float(loss.detach()) - float(ref.loss)) <= 2e-3 * abs(float(ref.loss)) + 1e-6
     assert O.rel_err(a.grad.cpu(), ref.d_image) <= 2e-3 and O.rel_err(b.grad.cpu(), ref.d_text) <= 2e-3
     assert abs(float(s.grad) - float(ref.d_logit_scale)) <= 2e-3 * abs(float(ref.d_logit_scale))
+
+
+@pytest.mark.parametrize("M,N,D", [(300, 1000, 512), (256, 2048, 768)])
+def test_block_grad_with_a_preconverted_f16_copy_is_bit_identical(M, N, D):
+    """mclip_block_grad(Y16 = mclip_convert_f16(Y)) == mclip_block_grad with its own conversion pass (bf16 inputs)."""
+    be = backend(TC)
+    x, y = feats(M, N, D, torch.bfloat16, seed=M + N, correlated=True)
+    lse_x, _ = O.block_row_lse(x.float(), y.float(), 20.0, None)
+    lse_y, _ = O.block_row_lse(y.float(), x.float(), 20.0, None)
+    xd, yd = x.cuda(), y.cuda()
+    args = (xd, yd, torch.tensor([20.0], device="cuda"), torch.tensor([1.0], device="cuda"), lse_x.float().cuda(),
+            lse_y.float().cuda(), 0, 1.0, 1.0, 2.0, 0.5 / M, True)
+    y16 = be.to_f16(yd)
+    assert y16.dtype == torch.float16 and torch.equal(y16.float(), yd.float())
+    dx0, rd0 = be.block_grad(*args)
+    dx1, rd1 = be.block_grad(*args, y16=y16)
+    assert torch.equal(dx0, dx1) and torch.equal(rd0, rd1)
