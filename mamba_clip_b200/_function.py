@@ -124,14 +124,14 @@ def _start_f16_copies(be, run, all_i, all_t, work_i, work_t):
     ps.wait_stream(torch.cuda.current_stream(dev))
     y16_t = run.buffer("y16_t", tuple(all_t.shape), torch.float16, dev)
     y16_i = run.buffer("y16_i", tuple(all_i.shape), torch.float16, dev)
-    y16_t.record_stream(ps)       # allocated on the compute stream, written on the side stream
-    y16_i.record_stream(ps)
     with torch.cuda.stream(ps):
+        # both copies start once BOTH gathers are done: a bandwidth kernel next to an NCCL LL all-gather slows the gather
+        # (measured: the image gather went 56 -> 113 us and delayed the statistics gather queued behind it)
         if work_t is not None:
             work_t.wait()
-        be.to_f16(all_t, out=y16_t)
         if work_i is not None:
             work_i.wait()
+        be.to_f16(all_t, out=y16_t)
         be.to_f16(all_i, out=y16_i)
         ev = torch.cuda.Event()
         ev.record(ps)
@@ -304,6 +304,10 @@ def _forward_impl(be, xi, xt, ls, local_loss, gather_with_grad, rank, W, group, 
         # the LSE vectors of the other ranks are only needed by backward: start the gather now, wait there
         stats = run.buffer("stats", (W, 2, Bl), torch.float32, dev)
         stats_work = _gather_into(stats, torch.stack((row_lse, col_lse)).unsqueeze(0), group, comm)
+    if f16_copies is not None:
+        # join: from here on the copies are ordered before everything the compute stream does next, so the buffers (allocated on
+        # the compute stream) need no record_stream bookkeeping even if the loss is dropped without a backward
+        torch.cuda.current_stream(dev).wait_event(f16_copies[2])
     return dict(loss=loss, xi=xi, xt=xt, all_i=all_i, all_t=all_t, ls=ls, row_lse=row_lse, col_lse=col_lse, diag=diag,
                 uv=uv, stats=stats, stats_work=stats_work, off=off, own_terms_only=own_terms_only,
                 row_lse_all=row_lse_all, col_lse_all=col_lse_all, f16_copies=f16_copies)
@@ -327,8 +331,7 @@ def _backward_impl(be, st, go, local_loss, gather_with_grad, W, group, need_i, n
     Bg = W * Bl
     y16_i = y16_t = None
     if st.get("f16_copies") is not None:
-        y16_i, y16_t, ev16 = st["f16_copies"]
-        torch.cuda.current_stream(xi.device).wait_event(ev16)
+        y16_i, y16_t, _ = st["f16_copies"]          # (the forward already joined the side stream)
 
     # 1/(2n) of the feature gradients: the true gradient for W=1 and (False, False),
     # W x that otherwise.

@@ -676,7 +676,8 @@ def test_block_grad_with_a_preconverted_f16_copy_is_bit_identical(M, N, D):
     args = (xd, yd, torch.tensor([20.0], device="cuda"), torch.tensor([1.0], device="cuda"), lse_x.float().cuda(),
             lse_y.float().cuda(), 0, 1.0, 1.0, 2.0, 0.5 / M, True)
     y16 = be.to_f16(yd)
-    assert y16.dtype == torch.float16 and torch.equal(y16.float(), yd.float())
+    # exact for normal f16 values; elements below 6.1e-5 land on the f16 subnormal grid (spacing 2^-24)
+    assert y16.dtype == torch.float16 and float((y16.float() - yd.float()).abs().max()) <= 2.0 ** -25
     dx0, rd0 = be.block_grad(*args)
     dx1, rd1 = be.block_grad(*args, y16=y16)
     assert torch.equal(dx0, dx1) and torch.equal(rd0, rd1)
