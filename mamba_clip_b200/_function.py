@@ -111,6 +111,10 @@ def _on_comm_stream(dev, fn):
 
 
 _prep_streams = {}
+# Opt-in (MCLIP_F16_PRECOPY=1, read once at import).  Measured on 2 GPUs at C3: hiding the two 11 us copies behind the forward
+# kernel does not pay -- whatever they overlap with on the memory system (the image all-gather: 56 -> 113 us; the statistics
+# all-gather: 9 -> 54 us) is an NCCL LL kernel on the critical path of the next segment; step 2.07 -> 2.08-2.16 ms.
+_F16_PRECOPY = os.environ.get("MCLIP_F16_PRECOPY", "0") == "1"
 
 
 def _start_f16_copies(be, run, all_i, all_t, work_i, work_t):
@@ -224,7 +228,7 @@ def _forward_impl(be, xi, xt, ls, local_loss, gather_with_grad, rank, W, group, 
         work_i = work_t = None
 
     f16_copies = None
-    if (for_backward and xi.dtype == torch.bfloat16 and dev.type == "cuda" and hasattr(be, "to_f16") and xi.shape[1] % 8 == 0 and xi.shape[1] <= 768
+    if (_F16_PRECOPY and for_backward and xi.dtype == torch.bfloat16 and dev.type == "cuda" and hasattr(be, "to_f16") and xi.shape[1] % 8 == 0 and xi.shape[1] <= 768
             and not torch.cuda.is_current_stream_capturing()
             and not (W == 1 and getattr(be, "fused_supported", lambda *_: False)(xi, all_t))):
         # (c10d handles -- the fallback collectives -- are waited for on the compute stream only)
