@@ -111,10 +111,15 @@ def _on_comm_stream(dev, fn):
 
 
 _prep_streams = {}
-# Opt-in (MCLIP_F16_PRECOPY=1, read once at import).  Measured on 2 GPUs at C3: hiding the two 11 us copies behind the forward
-# kernel does not pay -- whatever they overlap with on the memory system (the image all-gather: 56 -> 113 us; the statistics
-# all-gather: 9 -> 54 us) is an NCCL LL kernel on the critical path of the next segment; step 2.07 -> 2.08-2.16 ms.
-_F16_PRECOPY = os.environ.get("MCLIP_F16_PRECOPY", "0") == "1"
+# MCLIP_F16_PRECOPY = 1 / 0 forces it on / off (read once at import); default: on from 8 ranks.  Measured at C3: on 2 GPUs
+# hiding the two 11 us copies behind the forward kernel does NOT pay -- whatever they overlap with on the memory system (the
+# image all-gather: 56 -> 113 us; the statistics all-gather: 9 -> 54 us) is an NCCL LL kernel on the critical path of the next
+# segment, step 2.07 -> 2.08-2.16 ms; on 8 GPUs (4 MB shards, 0.75 ms steps) it does: 0.755 -> 0.727 ms (tools/r2_n8_matrix.sh).
+_F16_PRECOPY = {"1": True, "0": False}.get(os.environ.get("MCLIP_F16_PRECOPY", ""), None)
+
+
+def _f16_precopy(W: int) -> bool:
+    return _F16_PRECOPY if _F16_PRECOPY is not None else W >= 8
 
 
 def _start_f16_copies(be, run, all_i, all_t, work_i, work_t):
@@ -228,7 +233,7 @@ def _forward_impl(be, xi, xt, ls, local_loss, gather_with_grad, rank, W, group, 
         work_i = work_t = None
 
     f16_copies = None
-    if (_F16_PRECOPY and for_backward and xi.dtype == torch.bfloat16 and dev.type == "cuda" and hasattr(be, "to_f16") and xi.shape[1] % 8 == 0 and xi.shape[1] <= 768
+    if (_f16_precopy(W) and for_backward and xi.dtype == torch.bfloat16 and dev.type == "cuda" and hasattr(be, "to_f16") and xi.shape[1] % 8 == 0 and xi.shape[1] <= 768
             and not torch.cuda.is_current_stream_capturing()
             and not (W == 1 and getattr(be, "fused_supported", lambda *_: False)(xi, all_t))):
         # (c10d handles -- the fallback collectives -- are waited for on the compute stream only)
