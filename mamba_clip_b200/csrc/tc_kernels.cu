@@ -2929,8 +2929,10 @@ int launch_convert_f16(const void* src, int64_t rows, int64_t D, int64_t ld, voi
 bool tc_fused_supported(int64_t M, int64_t N, int64_t D, int64_t ldx, int64_t ldy, int dtype) {
   if (!options().fused_bwd) return false;
   if (!tc_supported(M, N, D, ldx, ldy, dtype, MCLIP_OP_BLOCK_GRAD) || D > 512) return false;
-  // pays off once a panel launch is long enough to hide its prologue / drain: >= 16 steps per CTA, >= 2 panels' worth of rows
-  return N >= 8192 && M >= 2048;
+  // pays off once the panel launches are long enough to hide their prologue / drain and the strip round trip; measured
+  // (tools/one_fused.py, square problems): B = 8192: 0.243 ms vs 0.221 ms for two recompute launches (loses), B = 16384:
+  // 0.694 vs 0.868 ms, B = 32768: 2.65 vs 2.88 ms
+  return N >= 16384 && M >= 4096;
 }
 
 size_t tc_fused_grad_ws(int64_t M, int64_t N, int64_t D) {

@@ -518,11 +518,12 @@ def test_fused_grad(dtype, M, N, D, ls, diag_off):
 
 
 def test_fused_backward_matches_two_launch_backward():
-    """ClipLoss at a size where the shared-recompute backward is chosen (W = 1, B >= 8192) against the same loss with the
+    """ClipLoss at a size where the shared-recompute backward is chosen (W = 1, B >= 16384) against the same loss with the
     option switched off (two recompute launches): same loss, gradients within bf16 rounding of each other."""
     from mamba_clip_b200 import ClipLoss, _cabi
     be = _cabi.get_backend()
-    img, txt = O.make_features(8192, 512, seed=17, dtype=torch.bfloat16)
+    img, txt = O.make_features(16384, 512, seed=17, dtype=torch.bfloat16)
+    assert be.fused_supported(img.cuda(), txt.cuda())
     outs = []
     for fused in (1, 0):
         be.set_option("fused_bwd", fused)
