@@ -2770,6 +2770,10 @@ FusedPlan plan_fused(int64_t M, int64_t N, int64_t D) {
   return f;
 }
 
+// G strips / partial-sum buffers in flight.  Two suffice: a third one (so that the recompute launch of panel p+2 need not wait
+// for the dY GEMM of panel p and can fill the SMs that GEMM's second round leaves idle) was measured and changes nothing
+// (2.64 vs 2.65 ms per call at C3) -- the call is bound by total tensor / L2-port work, not by launch-level gaps.
+constexpr int kFusedBufs = 2;
 struct FusedWs { size_t stat, y16, x16, acc_y, acc_x, g, total; };
 FusedWs fused_ws_layout(const FusedPlan& f, int64_t M, int64_t N, int64_t D, bool bf) {
   FusedWs w;
@@ -2778,8 +2782,8 @@ FusedWs fused_ws_layout(const FusedPlan& f, int64_t M, int64_t N, int64_t D, boo
   w.y16 = off;   off += bf ? align_up((size_t)N * D * 2, 256) : 0;
   w.x16 = off;   off += bf ? align_up((size_t)M * D * 2, 256) : 0;
   w.acc_y = off; off += align_up((size_t)N * D * sizeof(float), 256);
-  w.acc_x = off; off += 2 * align_up((size_t)f.b.nsplit * f.panel_rows * D * sizeof(float), 256);   // double-buffered
-  w.g = off;     off += 2 * align_up((size_t)f.panel_rows * f.n_pad * 2, 1024);
+  w.acc_x = off; off += kFusedBufs * align_up((size_t)f.b.nsplit * f.panel_rows * D * sizeof(float), 256);
+  w.g = off;     off += kFusedBufs * align_up((size_t)f.panel_rows * f.n_pad * 2, 1024);
   w.total = off;
   return w;
 }
@@ -2880,9 +2884,10 @@ int fused_grad_impl(const FusedGradArgs& a) {
   for (int pi = 0; pi < f.panels; ++pi) {
     const int64_t r0 = (int64_t)pi * f.panel_rows;
     const int64_t rows = (a.M - r0 < f.panel_rows) ? a.M - r0 : f.panel_rows;
-    void* gbuf = ws + w.g + (size_t)(pi & 1) * g_stride;
-    float* acc_x = reinterpret_cast<float*>(ws + w.acc_x + (size_t)(pi & 1) * accx_stride);
-    if (pi >= 2) MCLIP_CUDA_OK(cudaStreamWaitEvent(a.stream, fs->ev[2 * (pi - 2) + 1], 0));   // G and partial buffers free again
+    void* gbuf = ws + w.g + (size_t)(pi % kFusedBufs) * g_stride;
+    float* acc_x = reinterpret_cast<float*>(ws + w.acc_x + (size_t)(pi % kFusedBufs) * accx_stride);
+    if (pi >= kFusedBufs)       // G and partial buffers of panel pi - kFusedBufs are free again once its dY GEMM is done
+      MCLIP_CUDA_OK(cudaStreamWaitEvent(a.stream, fs->ev[2 * (pi - kFusedBufs) + 1], 0));
     BlockGradArgs gp = g;
     gp.X = reinterpret_cast<const T*>(a.X) + r0 * a.ldx;
     gp.M = rows;
