@@ -2807,7 +2807,8 @@ int fused_streams(int nev, FusedStreams** out) {
   return MCLIP_OK;
 }
 
-// sum of the column-split partials -> dX (input dtype) and xdot[row] = <X[row], sum> / 2^12; one warp per row
+// sum of the column-split partials -> dX (input dtype) and xdot[row] = <X[row], sum> / 2^12; one warp per row, 8 elements
+// per lane and iteration (two float4 per partial, one 16-byte load of X, one 16-byte store of dX)
 template <typename T>
 __global__ void __launch_bounds__(256)
 acc_to_dx_dot_kernel(const float* __restrict__ acc, int nsplit, int64_t M, int64_t D, const T* __restrict__ X, int64_t ldx,
@@ -2819,19 +2820,26 @@ acc_to_dx_dot_kernel(const float* __restrict__ acc, int nsplit, int64_t M, int64
   const int64_t n = M * D;
   for (int64_t r = warp; r < M; r += nwarps) {
     float dot = 0.f;
-    for (int64_t d = lane * 4; d < D; d += 128) {     // D % 8 == 0 on this path
+    for (int64_t d = lane * 8; d < D; d += 256) {     // D % 8 == 0 and 16-byte aligned rows on this path
       const int64_t i = r * D + d;
-      float4 a = *reinterpret_cast<const float4*>(acc + i);
+      float4 a0 = *reinterpret_cast<const float4*>(acc + i), a1 = *reinterpret_cast<const float4*>(acc + i + 4);
       for (int s = 1; s < nsplit; ++s) {
-        const float4 b = *reinterpret_cast<const float4*>(acc + (int64_t)s * n + i);
-        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        const float4 b0 = *reinterpret_cast<const float4*>(acc + (int64_t)s * n + i);
+        const float4 b1 = *reinterpret_cast<const float4*>(acc + (int64_t)s * n + i + 4);
+        a0.x += b0.x; a0.y += b0.y; a0.z += b0.z; a0.w += b0.w;
+        a1.x += b1.x; a1.y += b1.y; a1.z += b1.z; a1.w += b1.w;
       }
-      const T* x = X + r * ldx + d;
-      dot = fmaf(a.x, to_f32<T>(x[0]), dot); dot = fmaf(a.y, to_f32<T>(x[1]), dot);
-      dot = fmaf(a.z, to_f32<T>(x[2]), dot); dot = fmaf(a.w, to_f32<T>(x[3]), dot);
-      T* o = dX + r * lddx + d;
-      o[0] = from_f32<T>(a.x * alpha); o[1] = from_f32<T>(a.y * alpha);
-      o[2] = from_f32<T>(a.z * alpha); o[3] = from_f32<T>(a.w * alpha);
+      const float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const uint4 xin = *reinterpret_cast<const uint4*>(X + r * ldx + d);
+      const T* xe = reinterpret_cast<const T*>(&xin);
+      uint4 out;
+      T* oe = reinterpret_cast<T*>(&out);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        dot = fmaf(v[e], to_f32<T>(xe[e]), dot);
+        oe[e] = from_f32<T>(v[e] * alpha);
+      }
+      *reinterpret_cast<uint4*>(dX + r * lddx + d) = out;
     }
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
