@@ -64,6 +64,8 @@ def _worker(rank, W, port, jobs, q):
                 os.environ["MCLIP_NO_SMALL_PATH"] = "1"
             else:
                 os.environ.pop("MCLIP_NO_SMALL_PATH", None)
+            # "precopy": force the f16 operand copies onto the side stream next to the forward (default only from 8 ranks)
+            mamba_clip_b200._function._F16_PRECOPY = True if job.get("precopy") else None
             reps = 5 if job.get("graphs") else 1
             Bl, D = job["Bl"], job["D"]
             dtype = getattr(torch, job["dtype"])
@@ -183,6 +185,9 @@ def test_nccl_two_ranks_ragged_shapes_and_forced_fallback():
                      no_small=True))
     jobs.append(dict(Bl=1000, D=96, dtype="float16", seed=6, corr=True, ls=100.0, go=1.0, local_loss=False, gwg=True, adv=True))
     jobs.append(dict(Bl=200, D=96, dtype="bfloat16", seed=8, corr=True, ls=20.0, go=2.0, local_loss=False, gwg=False))   # latency path, ragged
+    for Bl, D, mode in ((300, 200, (True, True)), (1000, 512, (False, False)), (256, 768, (True, True))):
+        jobs.append(dict(Bl=Bl, D=D, dtype="bfloat16", seed=300 + Bl, corr=True, ls=20.0, go=2.0, local_loss=mode[0], gwg=mode[1],
+                         no_small=True, precopy=True))                   # f16 copies made on the side stream
     out = _run(W, jobs)
     for j, job in enumerate(jobs):
         img, txt = _features(W, job)
