@@ -81,6 +81,7 @@ class _Done:
 
 
 _comm_streams = {}
+_NCCL_DEBUG_TIMEOUT_S = float(os.environ.get("MCLIP_NCCL_TIMEOUT_S", "0") or 0)      # read once at import
 
 
 class _EventWait:
@@ -107,6 +108,16 @@ def _on_comm_stream(dev, fn):
         fn()
         ev = torch.cuda.Event()
         ev.record(cs)
+    if _NCCL_DEBUG_TIMEOUT_S > 0:
+        # opt-in debugging aid (MCLIP_NCCL_TIMEOUT_S): the direct communicator has no watchdog, so a rank that never reaches the
+        # collective would otherwise show up as a silent hang.  Host-synchronous: not for production runs.
+        import time
+        t0 = time.monotonic()
+        while not ev.query():
+            if time.monotonic() - t0 > _NCCL_DEBUG_TIMEOUT_S:
+                raise RuntimeError(f"mamba_clip_b200: a direct NCCL collective did not complete within {_NCCL_DEBUG_TIMEOUT_S:.0f} s "
+                                   "(a rank is missing from the collective, or ranks disagree on its size)")
+            time.sleep(0.0005)
     return _EventWait(ev)
 
 
