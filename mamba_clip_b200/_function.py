@@ -565,8 +565,7 @@ class ClipLossFunction(torch.autograd.Function):
 
         ctx.graphed = None
         # the latency path is two kernels: replaying them from a graph would only add the static-buffer copies
-        small = (dev.type == "cuda" and _cabi._override is None
-                 and be.small_supported(xi.shape[0], W * xi.shape[0], xi.shape[1], cdt))
+        small = getattr(be, "small_supported", lambda *_: False)(xi.shape[0], W * xi.shape[0], xi.shape[1], cdt)
         if (_GRAPHS_ENABLED and not small and dev.type == "cuda" and _cabi._override is None
                 and xi.shape[0] * xi.shape[0] * W * xi.shape[1] < _GRAPH_MAX_WORK
                 and not torch.cuda.is_current_stream_capturing()):
@@ -763,7 +762,7 @@ def _check_equal_shards(x: torch.Tensor, group) -> None:
     """Every rank must bring the same [B_l, D] and dtype: the flat all-gather and the fixed row offsets `rank * B_l`
     silently corrupt (or hang) otherwise, where the reference would fail inside torch.  Checked with one tiny MIN/MAX
     all-reduce the first time a (group, shape, dtype) is seen -- one host synchronisation per new shape, none per step."""
-    key = (id(group), tuple(x.shape), x.dtype, x.device)
+    key = (group, tuple(x.shape), x.dtype, x.device)      # the group object itself: its id cannot be reused while the key lives
     if key in _checked_shards:
         return
     code = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}.get(x.dtype, 3)

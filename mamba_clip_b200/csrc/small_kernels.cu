@@ -13,9 +13,8 @@
 // fp32 arithmetic throughout, so fp32 inputs keep the 1e-5 bar and bf16/f16 inputs are exact products.
 // Rows are addressed through a blocked layout (row g lives at base + (g / Bl) * blk_stride + (g % Bl) * D) so that the
 // kernels read the all-gather receive buffer [W][image shard; text shard] directly.
-#include <atomic>
-
 #include "common.cuh"
+#include "tc_host.cuh"
 
 namespace mclip {
 
@@ -476,11 +475,8 @@ static int small_backward_t(const SmallArgs& a) {
   p.cols_per_split = (int)(ceil_div(ceil_div(a.Bg, kBC), p.cs) * kBC);
   p.cs = (int)ceil_div(a.Bg, p.cols_per_split);
   const size_t smem = ((size_t)(kBR + kBC) * (a.D + 4) + kBR * (kBC + 1)) * sizeof(float);
-  static std::atomic<size_t> configured{0};
-  if (configured.load() < smem) {
-    MCLIP_CUDA_OK(cudaFuncSetAttribute(small_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured.store(smem);
-  }
+  int rc = tc_set_smem(reinterpret_cast<const void*>(small_bwd_kernel<T>), (uint32_t)smem);   // once per (kernel, device)
+  if (rc) return rc;
   const dim3 grid((unsigned)p.cs, (unsigned)rtiles, 2);
   small_bwd_kernel<T><<<grid, 256, smem, a.stream>>>(p);
   count_launch();

@@ -73,6 +73,49 @@ class EmulatedFusedBackend(EmulatedBackend):
         return (alpha * (G @ Yd)).to(X.dtype), (alpha * (G.T @ Xd)).to(X.dtype), (G * C).sum(dim=1).float()
 
 
+class EmulatedSmallBackend(EmulatedBackend):
+    """Adds the oracle statement of the latency-path primitives (include/mclip_b200.h: mclip_small_pack / _forward /
+    _backward) so that its host logic -- ONE packed all-gather, the blocked [W][2][Bl][D] layout, the per-mode row ranges,
+    weights and scale factors, no scalar collectives -- runs on CPU under gloo."""
+
+    def small_supported(self, Bl, Bg, D, dtype):
+        return Bg <= 1024 and D <= 512
+
+    def small_pack(self, a, b, out_dtype):
+        self.calls.append("small_pack")
+        return torch.stack((a, b)).to(out_dtype)
+
+    @staticmethod
+    def _rows(A, Bm, Bl, Bg, D, stride):
+        W = Bg // Bl
+        if W == 1:
+            return A.reshape(Bg, D).double(), Bm.reshape(Bg, D).double()
+        recv = A.reshape(W, 2, Bl, D)
+        return recv[:, 0].reshape(Bg, D).double(), recv[:, 1].reshape(Bg, D).double()
+
+    def small_forward(self, A, Bm, Bl, Bg, D, blk_stride, ls, lo, hi):
+        self.calls.append("small_forward")
+        I, T = self._rows(A, Bm, Bl, Bg, D, blk_stride)
+        st = O.global_stats(I, T, float(ls))
+        stats = torch.empty(5 * Bg + 2, dtype=torch.float32)
+        for k, v in enumerate((st.row_lse, st.col_lse, st.diag, st.u, st.v)):
+            stats[k * Bg:(k + 1) * Bg] = v.float()
+        per_row = (st.row_lse - float(ls) * st.diag) + (st.col_lse - float(ls) * st.diag)
+        stats[5 * Bg] = float(per_row[lo:hi].sum() / (2 * (hi - lo)))
+        stats[5 * Bg + 1] = float((st.u + st.v - 2 * st.diag)[lo:hi].sum())
+        return stats
+
+    def small_backward(self, A, Bm, Bl, Bg, D, blk_stride, ls, go, stats, off, w_row, w_col, w_diag, inv_2n, dls_scale):
+        self.calls.append("small_backward")
+        I, T = self._rows(A, Bm, Bl, Bg, D, blk_stride)
+        row_lse, col_lse = stats[:Bg].double(), stats[Bg:2 * Bg].double()
+        alpha = float(go) * float(ls) * inv_2n
+        dA, _ = O.block_grad(I[off:off + Bl], T, float(ls), row_lse[off:off + Bl], col_lse, off, w_row, w_col, w_diag, alpha)
+        dB, _ = O.block_grad(T[off:off + Bl], I, float(ls), col_lse[off:off + Bl], row_lse, off, w_row, w_col, w_diag, alpha)
+        dls = torch.tensor([float(go) * dls_scale * float(stats[5 * Bg + 1])])
+        return dA.to(A.dtype), dB.to(A.dtype), dls
+
+
 LOG2E = 1.4426950408889634
 LN2 = 0.6931471805599453
 SUM_LO, SUM_HI = 2.0 ** -75, 2.0 ** 120

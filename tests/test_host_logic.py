@@ -149,7 +149,8 @@ def _worker(rank, case, port, q):
     try:
         from mamba_clip_b200 import ClipLoss, _cabi
         from tests._emul import EmulatedBackend, EmulatedPairBackend
-        be = EmulatedPairBackend() if case.get("pair") else EmulatedBackend()
+        from tests._emul import EmulatedSmallBackend
+        be = EmulatedSmallBackend() if case.get("small") else (EmulatedPairBackend() if case.get("pair") else EmulatedBackend())
         _cabi.set_backend_override(be)
         W, Bl = case["W"], case["Bl"]
         img, txt = O.make_features(W * Bl, case["D"], seed=case["seed"], correlated=case["corr"])
@@ -336,3 +337,25 @@ def test_gloo_unequal_shards_raise_on_every_rank():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all("same shape" in m for m in res.values()), res
+
+
+@pytest.mark.parametrize("k", [k for k, c in enumerate(RANK_CASES) if c["W"] == 2 or k % 4 == 1])
+def test_gloo_latency_path_against_golden(k):
+    """The latency path's host logic (B_g <= 1024: ONE packed all-gather, every rank evaluates the whole problem, per-mode
+    row ranges / weights / scale factors, no scalar collectives) with the oracle statement of its primitives, against the
+    reference's own gloo outputs for all four (local_loss, gather_with_grad) modes at 2 and 4 ranks."""
+    case = dict(RANK_CASES[k], small=True)
+    res = _run_ranks(case)
+    Bl = case["Bl"]
+    floor = grad_floor(case["go"], case["ls"], Bl)
+    for rank, loss, di, dt, dls, calls in res:
+        gl = float(RANKS[f"c{k}_r{rank}_loss"])
+        gd = float(RANKS[f"c{k}_r{rank}_dls"])
+        gi = torch.from_numpy(RANKS[f"c{k}_r{rank}_di"]).double()
+        gt = torch.from_numpy(RANKS[f"c{k}_r{rank}_dt"]).double()
+        assert abs(loss - gl) <= 3e-6 * max(1.0, abs(gl)) + 2e-7
+        assert abs(dls - gd) <= 3e-5 * abs(gd) + 1.2e-7 * case["go"] * max(1.0, case["ls"])
+        assert float((torch.from_numpy(di).double() - gi).norm()) <= 2e-5 * float(gi.norm()) + floor
+        assert float((torch.from_numpy(dt).double() - gt).norm()) <= 2e-5 * float(gt.norm()) + floor
+        # exactly: pack, forward, backward -- and nothing else from the library
+        assert calls == ["small_pack", "small_forward", "small_backward"], calls
