@@ -546,6 +546,25 @@ class _GraphedLoss:
         return tuple(None if o is None else o.clone() for o in outs)
 
 
+def _as_compute(t: torch.Tensor, cdt: torch.dtype) -> torch.Tensor:
+    """Detached, contiguous, in the compute dtype -- without the no-op `.to()` / `.contiguous()` calls when the tensor already
+    is (the latency configurations are host-bound: every tensor-method call is ~1-3 us of their step)."""
+    t = t.detach()
+    if t.dtype != cdt:
+        t = t.to(cdt)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _as_scalar(x, dev) -> torch.Tensor:
+    """[1] f32 device tensor view / copy of a 0-dim tensor or Python number."""
+    if torch.is_tensor(x):
+        x = x.detach()
+        if x.dtype != torch.float32 or x.device != dev:
+            x = x.to(device=dev, dtype=torch.float32)
+        return x.reshape(1)
+    return torch.full((1,), float(x), dtype=torch.float32, device=dev)
+
+
 class ClipLossFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, image_features, text_features, logit_scale, local_loss, gather_with_grad, rank, world_size,
@@ -553,12 +572,9 @@ class ClipLossFunction(torch.autograd.Function):
         be = _cabi.get_backend()
         dev = image_features.device
         cdt = _compute_dtype(image_features)
-        xi = image_features.detach().to(cdt).contiguous()
-        xt = text_features.detach().to(cdt).contiguous()
-        if torch.is_tensor(logit_scale):
-            ls = logit_scale.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
-        else:
-            ls = torch.full((1,), float(logit_scale), dtype=torch.float32, device=dev)
+        xi = _as_compute(image_features, cdt)
+        xt = _as_compute(text_features, cdt)
+        ls = _as_scalar(logit_scale, dev)
         W = int(world_size)
         need_ls = torch.is_tensor(logit_scale) and logit_scale.requires_grad
         wants_grad = need_ls or image_features.requires_grad or text_features.requires_grad
@@ -620,14 +636,16 @@ class ClipLossFunction(torch.autograd.Function):
             st = dict(ctx.state)
             if not st.get("small"):
                 st.update(zip(_SAVED_KEYS, ctx.saved_tensors))
-            go = grad_out.detach().to(device=st["xi"].device, dtype=torch.float32).reshape(1).contiguous()
+            go = _as_scalar(grad_out, st["xi"].device)
             d_img, d_txt, d_ls = _backward_impl(be, st, go, local_loss, gather_with_grad, W, group, need_i, need_t, need_ls)
         if d_ls is not None:
             dt, shape, dev = ctx.ls_meta
-            d_ls = d_ls.reshape(shape).to(device=dev, dtype=dt)
-        if d_img is not None:
+            d_ls = d_ls.reshape(shape)
+            if d_ls.dtype != dt or d_ls.device != dev:
+                d_ls = d_ls.to(device=dev, dtype=dt)
+        if d_img is not None and d_img.dtype != ctx.in_dtypes[0]:
             d_img = d_img.to(ctx.in_dtypes[0])
-        if d_txt is not None:
+        if d_txt is not None and d_txt.dtype != ctx.in_dtypes[1]:
             d_txt = d_txt.to(ctx.in_dtypes[1])
         return d_img, d_txt, d_ls, None, None, None, None, None
 
