@@ -142,55 +142,90 @@ def _free_port():
     return p
 
 
-def _worker(rank, case, port, q):
+def _run_case(rank, case):
+    from mamba_clip_b200 import ClipLoss, _cabi
+    from tests._emul import EmulatedBackend, EmulatedPairBackend, EmulatedSmallBackend
+    be = EmulatedSmallBackend() if case.get("small") else (EmulatedPairBackend() if case.get("pair") else EmulatedBackend())
+    _cabi.set_backend_override(be)
+    W, Bl = case["W"], case["Bl"]
+    img, txt = O.make_features(W * Bl, case["D"], seed=case["seed"], correlated=case["corr"])
+    if case.get("adv"):
+        # identical pairs (cos = 1), then the first half of the image rows shrunk: at ls = 100 the columns of the
+        # first half see nothing within ~80 log2 units of the other half's positives -> out of the f32 window
+        txt = img.clone()
+        img[: W * Bl // 2] *= 0.01
+    img = img[rank * Bl:(rank + 1) * Bl].clone().requires_grad_(True)
+    txt = txt[rank * Bl:(rank + 1) * Bl].clone().requires_grad_(True)
+    ls = torch.tensor(case["ls"], requires_grad=True)
+    crit = ClipLoss(case["local_loss"], case["gwg"], True, rank, W)
+    loss = crit(img, txt, ls)["contrastive_loss"]
+    loss.backward(torch.tensor(case["go"]))
+    return (rank, float(loss), img.grad.numpy(), txt.grad.numpy(), float(ls.grad), list(be.calls))
+
+
+def _worker(rank, world, jobs, port, q):
+    """One process per rank runs EVERY job of its world size (a spawn costs ~10 s of interpreter + torch start-up, the jobs
+    themselves milliseconds): fresh ClipLoss and fresh emulated backend per job, one process group for all of them."""
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=case["W"])
+    dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        from mamba_clip_b200 import ClipLoss, _cabi
-        from tests._emul import EmulatedBackend, EmulatedPairBackend
-        from tests._emul import EmulatedSmallBackend
-        be = EmulatedSmallBackend() if case.get("small") else (EmulatedPairBackend() if case.get("pair") else EmulatedBackend())
-        _cabi.set_backend_override(be)
-        W, Bl = case["W"], case["Bl"]
-        img, txt = O.make_features(W * Bl, case["D"], seed=case["seed"], correlated=case["corr"])
-        if case.get("adv"):
-            # identical pairs (cos = 1), then the first half of the image rows shrunk: at ls = 100 the columns of the
-            # first half see nothing within ~80 log2 units of the other half's positives -> out of the f32 window
-            txt = img.clone()
-            img[: W * Bl // 2] *= 0.01
-        img = img[rank * Bl:(rank + 1) * Bl].clone().requires_grad_(True)
-        txt = txt[rank * Bl:(rank + 1) * Bl].clone().requires_grad_(True)
-        ls = torch.tensor(case["ls"], requires_grad=True)
-        crit = ClipLoss(case["local_loss"], case["gwg"], True, rank, W)
-        loss = crit(img, txt, ls)["contrastive_loss"]
-        loss.backward(torch.tensor(case["go"]))
-        q.put((rank, float(loss), img.grad.numpy(), txt.grad.numpy(), float(ls.grad), list(be.calls)))
+        out = {}
+        for key, case in jobs:
+            out[key] = _run_case(rank, case)
+            dist.barrier()
+        q.put((rank, out))
         dist.barrier()
     finally:
         dist.destroy_process_group()
 
 
-def _run_ranks(case):
+def _spawn_jobs(world, jobs):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, case, port, q)) for r in range(case["W"])]
+    procs = [ctx.Process(target=_worker, args=(r, world, jobs, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = sorted([q.get(timeout=180) for _ in procs], key=lambda t: t[0])
+    per_rank = dict(q.get(timeout=600) for _ in procs)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    return res
+    return {key: [per_rank[r][key] for r in range(world)] for key, _ in jobs}
 
 
-@pytest.mark.parametrize("k", [k for k, c in enumerate(RANK_CASES) if c["W"] == 2 or k % 4 == 0])
+_PAIR_KS = [k for k, c in enumerate(RANK_CASES) if c["W"] == 2 or k % 4 == 0]
+_SMALL_KS = [k for k, c in enumerate(RANK_CASES) if c["W"] == 2 or k % 4 == 1]
+_ADV_CASE = dict(W=2, Bl=48, D=512, seed=7, corr=True, ls=100.0, go=2.0, local_loss=True, gwg=True, pair=True, adv=True)
+_golden_runs = {}
+
+
+def _golden_run(variant, k):
+    """Results of golden case k through the given host path ("plain" one-sided, "pair" two-sided forward, "small" latency
+    path, "adv" the out-of-window case); all jobs of one world size run in a single spawn the first time one is asked for."""
+    W = _ADV_CASE["W"] if variant == "adv" else RANK_CASES[k]["W"]
+    if W not in _golden_runs:
+        jobs = []
+        for kk, c in enumerate(RANK_CASES):
+            if c["W"] != W:
+                continue
+            jobs.append((("plain", kk), c))
+            if kk in _PAIR_KS:
+                jobs.append((("pair", kk), dict(c, pair=True)))
+            if kk in _SMALL_KS:
+                jobs.append((("small", kk), dict(c, small=True)))
+        if W == _ADV_CASE["W"]:
+            jobs.append((("adv", 0), _ADV_CASE))
+        _golden_runs[W] = _spawn_jobs(W, jobs)
+    return _golden_runs[W][(variant, k)]
+
+
+@pytest.mark.parametrize("k", _PAIR_KS)
 def test_gloo_two_sided_forward_against_golden(k):
     """Same golden vectors through the two-sided forward host logic: per-rank column sums gathered and merged, status
     flag clean, predicated fallback calls skipped, text-side `v` taken from the backward launch."""
-    case = dict(RANK_CASES[k], pair=True)
-    res = _run_ranks(case)
+    case = RANK_CASES[k]
+    res = _golden_run("pair", k)
     Bl = case["Bl"]
     floor = grad_floor(case["go"], case["ls"], Bl)
     for rank, loss, di, dt, dls, calls in res:
@@ -209,8 +244,7 @@ def test_gloo_two_sided_forward_against_golden(k):
 def test_gloo_two_sided_forward_fallback_on_out_of_window_inputs():
     """ls = 100 and half of the global rows scaled by 0.01: the ranks whose columns fall out of the f32 window must
     take the predicated one-sided path and every rank must still reproduce the reference (oracle rank emulation)."""
-    case = dict(W=2, Bl=48, D=512, seed=7, corr=True, ls=100.0, go=2.0, local_loss=True, gwg=True, pair=True, adv=True)
-    res = _run_ranks(case)
+    res = _golden_run("adv", 0)
     img, _ = O.make_features(2 * 48, 512, seed=7, correlated=True)
     txt = img.clone()
     img[:48] *= 0.01
@@ -228,16 +262,7 @@ def test_gloo_two_sided_forward_fallback_on_out_of_window_inputs():
 @pytest.mark.parametrize("k", range(len(RANK_CASES)))
 def test_gloo_ranks_against_golden(k):
     case = RANK_CASES[k]
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, case, port, q)) for r in range(case["W"])]
-    for p in procs:
-        p.start()
-    res = sorted([q.get(timeout=180) for _ in procs], key=lambda t: t[0])
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    res = _golden_run("plain", k)
     Bl = case["Bl"]
     floor = grad_floor(case["go"], case["ls"], Bl)
     for rank, loss, di, dt, dls, _calls in res:
@@ -339,13 +364,13 @@ def test_gloo_unequal_shards_raise_on_every_rank():
     assert all("same shape" in m for m in res.values()), res
 
 
-@pytest.mark.parametrize("k", [k for k, c in enumerate(RANK_CASES) if c["W"] == 2 or k % 4 == 1])
+@pytest.mark.parametrize("k", _SMALL_KS)
 def test_gloo_latency_path_against_golden(k):
     """The latency path's host logic (B_g <= 1024: ONE packed all-gather, every rank evaluates the whole problem, per-mode
     row ranges / weights / scale factors, no scalar collectives) with the oracle statement of its primitives, against the
     reference's own gloo outputs for all four (local_loss, gather_with_grad) modes at 2 and 4 ranks."""
-    case = dict(RANK_CASES[k], small=True)
-    res = _run_ranks(case)
+    case = RANK_CASES[k]
+    res = _golden_run("small", k)
     Bl = case["Bl"]
     floor = grad_floor(case["go"], case["ls"], Bl)
     for rank, loss, di, dt, dls, calls in res:
