@@ -194,8 +194,8 @@ def _spawn_jobs(world, jobs):
     return {key: [per_rank[r][key] for r in range(world)] for key, _ in jobs}
 
 
-_PAIR_KS = [k for k, c in enumerate(RANK_CASES) if c["W"] == 2 or k % 4 == 0]
-_SMALL_KS = [k for k, c in enumerate(RANK_CASES) if c["W"] == 2 or k % 4 == 1]
+_PAIR_KS = list(range(len(RANK_CASES)))
+_SMALL_KS = list(range(len(RANK_CASES)))
 _ADV_CASE = dict(W=2, Bl=48, D=512, seed=7, corr=True, ls=100.0, go=2.0, local_loss=True, gwg=True, pair=True, adv=True)
 _golden_runs = {}
 
