@@ -1,10 +1,13 @@
 // Tensor-core path of the contrastive-loss kernels for B200 (sm_100a):
 //   TMA (cp.async.bulk.tensor, SWIZZLE_128B) -> shared memory -> tcgen05.mma (bf16/f16, f32 accumulate
-//   in TMEM) -> tcgen05.ld epilogue warps.  The logits block only ever exists as 128 x BN f32 tiles in TMEM.
+//   in TMEM) -> tcgen05.ld epilogue warps.  The logits block only ever exists as f32 tiles in TMEM.
 //
-// Two kernels, both "one-sided" (rows of X against all rows of Y), see DESIGN.md:
-//   tc_row_lse_kernel     partial row (max, sum-exp) of ls * X Y^T           (forward)
-//   tc_block_grad_kernel  dX = alpha * G Y with G recomputed tile by tile     (backward)
+// "One-sided" kernels (rows of X against all rows of Y), see DESIGN.md section 3:
+//   tc_row_lse_kernel / tc_row_lse2_kernel   partial row (max, sum-exp) of ls * X Y^T  (forward: predicated fallback,
+//                                            local_loss=False rows; the two-sided forward lives in tc_pair_lse.cu)
+//   tc_block_grad2_kernel                    dX = alpha * G Y with G recomputed tile by tile, CTA pairs (backward);
+//                                            kStoreG also hands G to the TN GEMM of tc_gemm_tn.cu (mclip_fused_grad)
+//   tc_block_grad2p_kernel                   the same as a persistent kernel over (item, step) units (option bwd_persist)
 //
 // Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
 // warps 4..11 = epilogue (two warpgroups; warp w reads TMEM lanes 32*(w%4).. and one column half).
@@ -62,26 +65,6 @@ struct FwdParams {
   int bf16;
   int dbg;            // development switch (MCLIP_DBG & 16): print barrier-wait cycle counts of a few CTAs
   const int* run_if;  // device flag (null = always run): 0 makes the whole grid exit before touching anything
-};
-
-struct BwdParams {
-  int64_t M, N, D;
-  int kch;
-  int stages;
-  int steps_total;      // ceil(N / 128)
-  int steps_per_split;
-  int nsplit;
-  int64_t diag_off;
-  const float* ls;
-  const float* go;
-  const float* lse_x;
-  const float* lse_y;
-  float w_row, w_col, w_diag, inv_2n;
-  void* dX;
-  int64_t lddx;
-  float* acc_ws;        // f32 [nsplit][M, D] partial dX when nsplit > 1 (summed in fixed order afterwards)
-  float* rd_ws;         // f32 [nsplit][M] partial rowdot when nsplit > 1
-  float* rowdot;
 };
 
 __device__ __forceinline__ uint32_t align1024(uint32_t a) { return (a + 1023u) & ~1023u; }
@@ -488,315 +471,6 @@ tc_row_lse2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc_cg2(tmem_base, kTmemCols);
-  }
-}
-
-// =================================================================================================
-// backward
-// =================================================================================================
-// TMEM columns: S/G buffers [0,128) and [128,256); dX accumulator [256, 512).
-// G (16-bit, two per column) overwrites its own S buffer: warpgroup 0 owns S columns [0,64) -> G columns
-// [0,32); warpgroup 1 owns S columns [64,128) -> G columns [64,96).
-template <bool kGBF16, bool kMasked, bool kCol>
-__device__ __forceinline__ void bwd_chunk(const uint32_t (&v)[32], uint32_t (&g)[16], float k2, float lx2,
-                                          const float* __restrict__ ly2, float lw_diag, int64_t col0, int64_t N,
-                                          int64_t jd, float& rd) {
-#pragma unroll
-  for (int j = 0; j < 32; j += 2) {
-    float gv[2];
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const float c = __uint_as_float(v[j + e]);
-      float p_row = ex2_approx(fmaf(c, k2, -lx2));
-      float gg = p_row;
-      if (kCol) gg += ex2_approx(fmaf(c, k2, -ly2[j + e]));
-      if (kMasked) {
-        if (col0 + j + e == jd) gg -= lw_diag;
-        if (col0 + j + e >= N) { gg = 0.f; p_row = 0.f; }
-      }
-      rd = fmaf(p_row, c, rd);
-      gv[e] = gg;
-    }
-    g[j >> 1] = kGBF16 ? pack_bf16x2(gv[0], gv[1]) : pack_f16x2(gv[0], gv[1]);
-  }
-}
-
-// Single-CTA version (any D <= 768; used for D > 512).  kGF16: G is written as f16 scaled by 2^12 and the dX MMA
-// reads the f16 copy of Y (tcgen05 kind::f16 raises an illegal-instruction fault for A = f16, B = bf16 -- measured).
-template <bool kBF16, bool XRES, bool kGF16>
-__global__ void __launch_bounds__(kThreads, 1)
-tc_block_grad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
-                     const __grid_constant__ CUtensorMap tmY16, const BwdParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = align1024(smem_u32(smem_raw));
-  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  constexpr uint32_t kStageBytes = kChunkBytes + (XRES ? 0u : kChunkBytes);
-  const uint32_t x_bytes = XRES ? (uint32_t)p.kch * kChunkBytes : 0u;
-  const int dc0 = blockIdx.y * 4;                       // first 64-wide d chunk of this CTA
-  const int ndc = min(4, p.kch - dc0);                  // d chunks handled here (N of the dX MMA = 64 * ndc)
-  const uint32_t yd_base = smem_base + x_bytes;         // [ndc][128 y][64 d], one buffer
-  const uint32_t ring_base = yd_base + 4 * kChunkBytes;
-  const uint32_t misc_base = ring_base + (uint32_t)p.stages * kStageBytes;
-  uint8_t* misc_gen = smem_gen + (misc_base - smem_base);
-  float* ly2_s = reinterpret_cast<float*>(misc_gen);  // [2][128]
-  const uint32_t bar_base = misc_base + 1024;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
-  const uint32_t xfull_bar = bar_base + 8u * (2 * kMaxStages);
-  auto sfull_bar = [&](int b) { return bar_base + 8u * (2 * kMaxStages + 1 + b); };
-  auto sempty_bar = [&](int b) { return bar_base + 8u * (2 * kMaxStages + 3 + b); };
-  auto gfull_bar = [&](int b) { return bar_base + 8u * (2 * kMaxStages + 5 + b); };
-  const uint32_t ydfull_bar = bar_base + 8u * (2 * kMaxStages + 7);
-  const uint32_t ydempty_bar = bar_base + 8u * (2 * kMaxStages + 8);
-  const uint32_t dxfull_bar = bar_base + 8u * (2 * kMaxStages + 9);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 10);
-  uint32_t* tmem_slot_gen = reinterpret_cast<uint32_t*>(misc_gen + 1024 + 8u * (2 * kMaxStages + 10));
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t m0 = (int64_t)blockIdx.x * 128;
-  const int s0 = blockIdx.z * p.steps_per_split;
-  const int s1 = min(p.steps_total, s0 + p.steps_per_split);
-  const int nsteps = s1 - s0;
-  constexpr uint32_t kTmemCols = 512;
-  constexpr uint32_t kDxCol = 256;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmX);
-    tma_prefetch_desc(&tmY);
-    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    mbar_init(xfull_bar, 1);
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(sfull_bar(b), 1);
-      mbar_init(sempty_bar(b), 1);
-      mbar_init(gfull_bar(b), kEpiThreads / 32);
-    }
-    mbar_init(ydfull_bar, 1);
-    mbar_init(ydempty_bar, 1);
-    mbar_init(dxfull_bar, 1);
-    fence_barrier_init();
-  } else if (warp == 2) {
-    tmem_alloc(tmem_slot, kTmemCols);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_gen;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      // ---------------- TMA producer ----------------
-      if (XRES) {
-        mbar_expect_tx(xfull_bar, x_bytes);
-        for (int c = 0; c < p.kch; ++c) tma_load_2d(smem_base + c * kChunkBytes, &tmX, c * 64, (int32_t)m0, xfull_bar);
-      }
-      uint32_t it = 0;
-      for (int ls_ = 0; ls_ < nsteps; ++ls_) {
-        const int32_t n0 = (s0 + ls_) * 128;
-        for (int c = 0; c < p.kch; ++c, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
-          mbar_wait(empty_bar(s), ph ^ 1);
-          mbar_expect_tx(full_bar(s), kStageBytes);
-          const uint32_t dst = ring_base + s * kStageBytes;
-          tma_load_2d(dst, &tmY, c * 64, n0, full_bar(s));
-          if (!XRES) tma_load_2d(dst + kChunkBytes, &tmX, c * 64, (int32_t)m0, full_bar(s));
-        }
-        // Y rows of this step again, as the [K = y][N = d] operand of the dX MMA (single buffer)
-        mbar_wait(ydempty_bar, (ls_ & 1) ^ 1);
-        mbar_expect_tx(ydfull_bar, (uint32_t)ndc * kChunkBytes);
-        for (int qd = 0; qd < ndc; ++qd) tma_load_2d(yd_base + qd * kChunkBytes, &tmY16, (dc0 + qd) * 64, n0, ydfull_bar);
-      }
-    }
-  } else if (warp == 1) {
-    {
-      // ---------------- MMA issuer: the whole warp waits, one elected lane issues ----------------
-      const bool elected = elect_one();
-      const uint32_t idesc_s = make_idesc_f16(kBF16, kBF16, 128, 128, false, false);
-      // with kGF16 both dX operands are f16: G, and the f16 copy of Y behind tmY16
-      const uint32_t idesc_dx = make_idesc_f16(kBF16 && !kGF16, kBF16 && !kGF16, 128, (uint32_t)ndc * 64, false, true);
-      if (XRES) mbar_wait(xfull_bar, 0);
-      uint32_t it = 0;
-      auto issue_s = [&](int ls_) {
-        const int buf = ls_ & 1;
-        const uint32_t bph = (ls_ >> 1) & 1;
-        mbar_wait(sempty_bar(buf), bph ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * 128;
-        for (int c = 0; c < p.kch; ++c, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
-          mbar_wait(full_bar(s), ph);
-          tc_fence_after();
-          const uint32_t b_addr = ring_base + s * kStageBytes;
-          const uint32_t a_addr = XRES ? (smem_base + c * kChunkBytes) : (b_addr + kChunkBytes);
-          if (elected) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t ad = make_smem_desc_sw128(a_addr + k * 32, 0, 1024);
-              const uint64_t bd = make_smem_desc_sw128(b_addr + k * 32, 0, 1024);
-              mma_ss(d_tmem, ad, bd, idesc_s, (c | k) != 0);
-            }
-            mma_commit(empty_bar(s));
-            if (c == p.kch - 1) mma_commit(sfull_bar(buf));
-          }
-          __syncwarp();
-        }
-      };
-      auto issue_dx = [&](int ls_) {
-        const int buf = ls_ & 1;
-        const uint32_t bph = (ls_ >> 1) & 1;
-        mbar_wait(gfull_bar(buf), bph);
-        mbar_wait(ydfull_bar, ls_ & 1);
-        tc_fence_after();
-        if (elected) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            // A = G[128 x 16] from TMEM (8 packed columns per k-step); B = Y[16 y][64*ndc d], MN-major:
-            // 64-wide d atoms are kChunkBytes apart (LBO), 8-row y groups 1024 B apart (SBO).
-            const uint32_t a_tmem = tmem_base + buf * 128 + (k < 4 ? k * 8 : 64 + (k - 4) * 8);
-            const uint64_t bd = make_smem_desc_sw128(yd_base + k * 2048, kChunkBytes, 1024);
-            mma_ts(tmem_base + kDxCol, a_tmem, bd, idesc_dx, (ls_ | k) != 0);
-          }
-          mma_commit(ydempty_bar);
-          mma_commit(sempty_bar(buf));
-          if (ls_ == nsteps - 1) mma_commit(dxfull_bar);
-        }
-        __syncwarp();
-      };
-      if (nsteps > 0) issue_s(0);
-      for (int ls_ = 0; ls_ < nsteps; ++ls_) {
-        if (ls_ + 1 < nsteps) issue_s(ls_ + 1);
-        issue_dx(ls_);
-      }
-    }
-  } else if (warp >= kEpiWarp0) {
-    // ---------------- epilogue: S -> G (16-bit, back into TMEM), then dX out ----------------
-    const int ew = warp - kEpiWarp0;
-    const int q = warp & 3;
-    const int half = ew >> 2;
-    const int et = threadIdx.x - kEpiWarp0 * 32;  // 0..255
-    const int row_in_tile = q * 32 + lane;
-    const int64_t row = m0 + row_in_tile;
-    const float ls = p.ls[0];
-    const float k2 = ls * kLog2e;
-    const bool has_col = p.w_col != 0.f;
-    // weights folded into the exponents: w * 2^a = 2^(a + log2 w)
-    constexpr bool kGBF16 = kBF16 && !kGF16;
-    constexpr float kGShift = kGF16 ? 12.f : 0.f;      // G is stored as G * 2^kGShift
-    constexpr float kGScale = kGF16 ? 4096.f : 1.f;
-    const float lw_row = log2f(p.w_row) + kGShift;
-    const float lw_col = (has_col ? log2f(p.w_col) : 0.f) + kGShift;
-    const float w_diag_s = p.w_diag * kGScale;
-    const float lx2 = (row < p.M ? p.lse_x[row] * kLog2e : 0.f) - lw_row;
-    const int64_t jd = row + p.diag_off;
-    float rd = 0.f;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    for (int ls_ = 0; ls_ < nsteps; ++ls_) {
-      const int buf = ls_ & 1;
-      const uint32_t bph = (ls_ >> 1) & 1;
-      const int64_t n0 = (int64_t)(s0 + ls_) * 128;
-      // stage lse_y (log2 units, weight folded) for this step; +inf for columns past N
-      if (has_col && et < 128) {
-        const int64_t col = n0 + et;
-        ly2_s[buf * 128 + et] = col < p.N ? p.lse_y[col] * kLog2e - lw_col : INFINITY;
-      }
-      named_bar_sync(1, kEpiThreads);
-      mbar_wait(sfull_bar(buf), bph);
-      tc_fence_after();
-      const bool special = (n0 + 128 > p.N) || (n0 < m0 + p.diag_off + 128 && n0 + 128 > m0 + p.diag_off);
-#pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
-        uint32_t v[32];
-        uint32_t g[16];
-        const int cbase = half * 64 + cc * 32;  // S column of this chunk
-        tmem_ld32(lane_addr + buf * 128 + cbase, v);
-        tmem_ld_wait();
-        const float* ly2 = ly2_s + buf * 128 + cbase;
-        const int64_t col0 = n0 + cbase;
-        if (special) {
-          if (has_col) bwd_chunk<kGBF16, true, true>(v, g, k2, lx2, ly2, w_diag_s, col0, p.N, jd, rd);
-          else bwd_chunk<kGBF16, true, false>(v, g, k2, lx2, ly2, w_diag_s, col0, p.N, jd, rd);
-        } else {
-          if (has_col) bwd_chunk<kGBF16, false, true>(v, g, k2, lx2, ly2, w_diag_s, col0, p.N, jd, rd);
-          else bwd_chunk<kGBF16, false, false>(v, g, k2, lx2, ly2, w_diag_s, col0, p.N, jd, rd);
-        }
-        tmem_st16(lane_addr + buf * 128 + half * 64 + cc * 16, g);
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(gfull_bar(buf));
-    }
-    // ---- dX accumulator -> global ----
-    mbar_wait(dxfull_bar, 0);
-    tc_fence_after();
-    const float alpha = (p.go ? p.go[0] : 1.f) * ls * p.inv_2n * (1.f / kGScale);
-    const int ncc = ndc;  // 32-column chunks per warpgroup: (ndc * 64 / 2) / 32
-    for (int cc = 0; cc < ncc; ++cc) {
-      uint32_t v[32];
-      const int cbase = half * (ndc * 32) + cc * 32;
-      tmem_ld32(lane_addr + kDxCol + cbase, v);
-      tmem_ld_wait();
-      const int64_t d0 = (int64_t)dc0 * 64 + cbase;
-      if (row < p.M && nsteps > 0) {
-        if (p.nsplit > 1) {
-          // this split's partial (unscaled, f32); summed over splits in fixed order by acc_to_dx_kernel
-          float* dst = p.acc_ws + ((int64_t)blockIdx.z * p.M + row) * p.D + d0;
-          if (d0 + 32 <= p.D) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<uint4*>(dst + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (d0 + j < p.D) dst[j] = __uint_as_float(v[j]);
-          }
-        } else if (d0 + 32 <= p.D) {
-          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.dX) + row * p.lddx + d0);
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 o;
-            float f[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j + e]) * alpha;
-            o.x = kBF16 ? pack_bf16x2(f[0], f[1]) : pack_f16x2(f[0], f[1]);
-            o.y = kBF16 ? pack_bf16x2(f[2], f[3]) : pack_f16x2(f[2], f[3]);
-            o.z = kBF16 ? pack_bf16x2(f[4], f[5]) : pack_f16x2(f[4], f[5]);
-            o.w = kBF16 ? pack_bf16x2(f[6], f[7]) : pack_f16x2(f[6], f[7]);
-            dst[j >> 3] = o;
-          }
-        } else {
-          uint16_t* dst = reinterpret_cast<uint16_t*>(p.dX) + row * p.lddx + d0;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (d0 + j < p.D) {
-              const uint32_t pk = kBF16 ? pack_bf16x2(__uint_as_float(v[j]) * alpha, 0.f)
-                                        : pack_f16x2(__uint_as_float(v[j]) * alpha, 0.f);
-              dst[j] = (uint16_t)(pk & 0xFFFFu);
-            }
-          }
-        }
-      }
-    }
-    // rowdot: add the two column halves through shared memory (fixed order), one value per row and split
-    if (p.rowdot != nullptr && blockIdx.y == 0) {
-      named_bar_sync(1, kEpiThreads);            // everyone is done with ly2_s
-      if (half == 1) ly2_s[row_in_tile] = rd;
-      named_bar_sync(1, kEpiThreads);
-      if (half == 0 && row < p.M) {
-        const float tot = (rd + ly2_s[row_in_tile]) * (1.f / kGScale);
-        if (p.nsplit > 1) p.rd_ws[(int64_t)blockIdx.z * p.M + row] = tot;
-        else p.rowdot[row] = tot;
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -1983,13 +1657,11 @@ struct Options {
   int bwd_persist;   // MCLIP_BWD_PERSIST: persistent CTA-pair backward kernel (stream-K vehicle)
   int dbg;           // MCLIP_DBG: development masks; only honoured by -DMCLIP_PROFILE builds
   int fused_bwd;     // MCLIP_FUSED_BWD: shared-recompute backward (one S recompute for dX and dY) where it applies
-  int bwd768_pair;   // MCLIP_BWD768_PAIR: CTA-pair backward kernel for 512 < D <= 768 (0: single-CTA kernel, one S recompute per 256-wide slice of D)
   Options() {
     auto geti = [](const char* k, int dflt) { const char* e = getenv(k); return e ? atoi(e) : dflt; };
     bwd_persist = geti("MCLIP_BWD_PERSIST", 0);
     dbg = kProfile ? geti("MCLIP_DBG", 0) : 0;
     fused_bwd = geti("MCLIP_FUSED_BWD", 1);
-    bwd768_pair = geti("MCLIP_BWD768_PAIR", 1);
   }
 };
 Options& options() {
@@ -2129,42 +1801,11 @@ FwdPlan plan_fwd2(int64_t M, int64_t N, int64_t D) {
   return f;
 }
 
-struct BwdPlan { bool xres; int stages; int kch; int dchunks; int steps_total; int nsplit; int steps_per_split; uint32_t smem; };
-
-BwdPlan plan_bwd(int64_t M, int64_t N, int64_t D) {
-  BwdPlan b;
-  b.kch = (int)ceil_div(D, 64);
-  b.xres = b.kch <= 8;
-  b.dchunks = (int)ceil_div(b.kch, 4);
-  const uint32_t avail = kSmemMax - kAlignSlack - kMiscBytes;
-  const uint32_t x_bytes = b.xres ? b.kch * kChunkBytes : 0;
-  const uint32_t stage = kChunkBytes + (b.xres ? 0 : kChunkBytes);
-  int st = (int)((avail - x_bytes - 4 * kChunkBytes) / stage);
-  b.stages = st > (int)kMaxStages ? (int)kMaxStages : st;
-  b.steps_total = (int)ceil_div(N, 128);
-  const int64_t items = ceil_div(M, 128) * b.dchunks;
-  int best = 1;
-  double best_cost = 1e30;
-  const int max_split = b.steps_total < 32 ? b.steps_total : 32;
-  for (int s = 1; s <= max_split; ++s) {
-    const int sps = (int)ceil_div(b.steps_total, s);
-    const int real = (int)ceil_div(b.steps_total, sps);
-    if (real != s) continue;
-    const double waves = (double)ceil_div(items * s, sm_count());
-    const double cost = waves * (sps + 3.0) + (s > 1 ? 0.02 * b.steps_total : 0.0);
-    if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
-  }
-  b.nsplit = best;
-  b.steps_per_split = (int)ceil_div(b.steps_total, best);
-  b.smem = kAlignSlack + x_bytes + 4 * kChunkBytes + b.stages * stage + kMiscBytes;
-  return b;
-}
-
 struct Bwd2Plan { int kch; int kpairs; int ndh; int steps_total; int nsplit; int steps_per_split; uint32_t smem; };
 
 // (Variants measured and removed in round 2, all numerically identical -- numbers in profiles/r1_ncu_summary.md section 3:
 // 4-CTA clusters with multicast Y tiles 1.95 vs 1.85 ms; G handed over through TMEM 1.61 vs 1.53 ms; transposed pair
-// kernel with a DSMEM exchange 1.98 vs 1.65 ms; single-CTA kernel at D <= 512 4.00 ms.)
+// kernel with a DSMEM exchange 1.98 vs 1.65 ms; single-CTA kernel 4.00 ms at D = 512 and 68.5 vs 25.1 ms per C4 step at D = 768.)
 Bwd2Plan plan_bwd2(int64_t M, int64_t N, int64_t D) {
   Bwd2Plan b;
   b.kch = (int)ceil_div(D, 64);
@@ -2382,7 +2023,6 @@ int tc_set_option(const char* name, int value) {
   if (k == "bwd_persist") o.bwd_persist = value;
   else if (k == "dbg") o.dbg = kProfile ? value : 0;
   else if (k == "fused_bwd") o.fused_bwd = value;
-  else if (k == "bwd768_pair") o.bwd768_pair = value;
   else { set_error("unknown option '%s'", name); return MCLIP_ERR_INVALID; }
   return MCLIP_OK;
 }
@@ -2393,7 +2033,6 @@ int tc_get_option(const char* name, int* value) {
   if (k == "bwd_persist") *value = o.bwd_persist;
   else if (k == "dbg") *value = o.dbg;
   else if (k == "fused_bwd") *value = o.fused_bwd;
-  else if (k == "bwd768_pair") *value = o.bwd768_pair;
   else { set_error("unknown option '%s'", name); return MCLIP_ERR_INVALID; }
   return MCLIP_OK;
 }
@@ -2412,23 +2051,13 @@ size_t tc_row_lse_ws(int64_t M, int64_t N, int64_t D) {
 }
 
 size_t tc_block_grad_ws(int64_t M, int64_t N, int64_t D) {
-  if (D <= 512) {
-    const Bwd2Plan b = plan_bwd2(M, N, D);
-    // dtype is not known here: always reserve room for the f16 copy of Y; cover both pair kernels
-    const size_t v2 = bwd_ws_layout(b.nsplit, M, N, D, (int64_t)b.steps_total * 256, true).total;
-    const int64_t n_pad = (int64_t)b.steps_total * 256, m_pad = ceil_div(M, 128) * 128;
-    const size_t v3 = (b.nsplit > 1 ? align_up((size_t)b.nsplit * M * D * sizeof(float), 256) : 0) +
-                      align_up(((size_t)2 * m_pad + 2 * (m_pad / 128) + n_pad + 2 * (n_pad / 128) + 64) * sizeof(float), 256) +
-                      align_up((size_t)N * D * 2, 256);
-    const size_t vp = bwd2p_ws_layout(pair_slots(), N, D, n_pad, true).total;
-    const size_t v23 = v2 > v3 ? v2 : v3;
-    return v23 > vp ? v23 : vp;
-  }
-  const BwdPlan b = plan_bwd(M, N, D);
-  const size_t v1 = (b.nsplit > 1 ? align_up((size_t)b.nsplit * M * (D + 1) * sizeof(float), 256) : 0) + align_up((size_t)N * D * 2, 256);
-  const Bwd2Plan b2 = plan_bwd2(M, N, D);
-  const size_t v2 = bwd_ws_layout(b2.nsplit, M, N, D, (int64_t)b2.steps_total * 256, true).total;
-  return v1 > v2 ? v1 : v2;
+  // dtype is not known here: always reserve room for the f16 copy of Y; cover both pair kernels
+  const Bwd2Plan b = plan_bwd2(M, N, D);
+  const int64_t n_pad = (int64_t)b.steps_total * 256;
+  const size_t v2 = bwd_ws_layout(b.nsplit, M, N, D, n_pad, true).total;
+  if (D > 512) return v2;
+  const size_t vp = bwd2p_ws_layout(pair_slots(), N, D, n_pad, true).total;
+  return v2 > vp ? v2 : vp;
 }
 
 int tc_row_lse(const RowLseArgs& a) {
@@ -2961,75 +2590,8 @@ int tc_fused_grad(const FusedGradArgs& a) {
 int tc_block_grad(const BlockGradArgs& a) {
   if (((uintptr_t)a.X | (uintptr_t)a.Y | (uintptr_t)a.dX) & 15) { set_error("block_grad(tcgen05): X/Y/dX must be 16-byte aligned"); return MCLIP_ERR_INVALID; }
   if (!(a.w_row > 0.f) || a.w_col < 0.f) { set_error("block_grad(tcgen05): needs w_row > 0 and w_col >= 0"); return MCLIP_ERR_INVALID; }
-  if (a.D <= 512) return use_persistent_bwd() ? tc_block_grad2p(a) : tc_block_grad2(a);
-  if (options().bwd768_pair) return tc_block_grad2(a);    // 512 < D <= 768: CTA-pair kernel with one S buffer
-  const BwdPlan b = plan_bwd(a.M, a.N, a.D);
-  if (b.stages < 2) { set_error("block_grad(tcgen05): not enough shared memory for D=%lld", (long long)a.D); return MCLIP_ERR_UNSUPPORTED; }
-  const bool bf = a.dtype == MCLIP_DTYPE_BF16;
-  const size_t acc_bytes = b.nsplit > 1 ? align_up((size_t)b.nsplit * a.M * (a.D + 1) * sizeof(float), 256) : 0;
-  const void* y16 = a.Y;
-  int64_t ld16 = a.ldy;
-  int rc;
-  if (bf && a.y16 != nullptr) {
-    y16 = a.y16;
-    ld16 = a.D;
-  } else if (bf) {
-    __half* dst = reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(a.ws) + acc_bytes);
-    const int64_t n8 = a.N * (a.D / 8);
-    const unsigned blocks = ew_blocks(n8, 256);
-    bf16_to_f16_kernel<<<blocks, 256, 0, a.stream>>>(reinterpret_cast<const __nv_bfloat16*>(a.Y), a.N, a.D, a.ldy, dst);
-    count_launch();
-    MCLIP_CUDA_OK(cudaGetLastError());
-    y16 = dst;
-    ld16 = a.D;
-  }
-  CUtensorMap tmX, tmY, tmY16;
-  rc = make_tmap(&tmX, a.X, a.M, a.D, a.ldx, a.dtype, 128);
-  if (rc) return rc;
-  rc = make_tmap(&tmY, a.Y, a.N, a.D, a.ldy, a.dtype, 128);
-  if (rc) return rc;
-  rc = make_tmap(&tmY16, y16, a.N, a.D, ld16, MCLIP_DTYPE_F16, 128);
-  if (rc) return rc;
-  BwdParams p;
-  p.M = a.M; p.N = a.N; p.D = a.D; p.kch = b.kch; p.stages = b.stages; p.steps_total = b.steps_total;
-  p.steps_per_split = b.steps_per_split; p.nsplit = b.nsplit; p.diag_off = a.diag_off; p.ls = a.logit_scale;
-  p.go = a.grad_out; p.lse_x = a.lse_x; p.lse_y = a.lse_y; p.w_row = a.w_row; p.w_col = a.w_col;
-  p.w_diag = a.w_diag; p.inv_2n = a.inv_2n; p.dX = a.dX; p.lddx = a.lddx;
-  p.acc_ws = reinterpret_cast<float*>(a.ws); p.rowdot = a.rowdot;
-  p.rd_ws = p.acc_ws + (size_t)b.nsplit * a.M * a.D;
-  dim3 grid((unsigned)ceil_div(a.M, 128), (unsigned)b.dchunks, (unsigned)b.nsplit);
-  const bool g_bf16 = false;   // G is always f16 * 2^12; bf16 inputs go through the f16 copy of Y
-#define MCLIP_LAUNCH_BWD(BF, XR, GF)                                                          \
-  do {                                                                                        \
-    rc = set_smem(tc_block_grad_kernel<BF, XR, GF>, b.smem);                                  \
-    if (rc) return rc;                                                                        \
-    tc_block_grad_kernel<BF, XR, GF><<<grid, kThreads, b.smem, a.stream>>>(tmX, tmY, tmY16, p); \
-  } while (0)
-  if (bf && b.xres && !g_bf16) MCLIP_LAUNCH_BWD(true, true, true);
-  else if (bf && b.xres) MCLIP_LAUNCH_BWD(true, true, false);
-  else if (bf && !g_bf16) MCLIP_LAUNCH_BWD(true, false, true);
-  else if (bf) MCLIP_LAUNCH_BWD(true, false, false);
-  else if (b.xres) MCLIP_LAUNCH_BWD(false, true, true);
-  else MCLIP_LAUNCH_BWD(false, false, true);
-#undef MCLIP_LAUNCH_BWD
-  count_launch();
-  MCLIP_CUDA_OK(cudaGetLastError());
-  if (b.nsplit > 1) {
-    const int64_t n = a.M * a.D;
-    const unsigned blocks = ew_blocks(n, 1024);
-    const float scale = a.inv_2n * (g_bf16 ? 1.f : 1.f / 4096.f);
-    if (bf)
-      acc_to_dx_kernel<__nv_bfloat16><<<blocks, 256, 0, a.stream>>>(p.acc_ws, p.rd_ws, b.nsplit, a.M, a.D, a.logit_scale,
-                                                                   a.grad_out, scale,
-                                                                   reinterpret_cast<__nv_bfloat16*>(a.dX), a.lddx, a.rowdot);
-    else
-      acc_to_dx_kernel<__half><<<blocks, 256, 0, a.stream>>>(p.acc_ws, p.rd_ws, b.nsplit, a.M, a.D, a.logit_scale,
-                                                            a.grad_out, scale, reinterpret_cast<__half*>(a.dX), a.lddx,
-                                                            a.rowdot);
-    count_launch();
-    MCLIP_CUDA_OK(cudaGetLastError());
-  }
-  return MCLIP_OK;
+  // D <= 512: both S buffers in TMEM; 512 < D <= 768: one S buffer, X tiles 8..11 resident too (kNX = 12)
+  return (a.D <= 512 && use_persistent_bwd()) ? tc_block_grad2p(a) : tc_block_grad2(a);
 }
 
 }  // namespace mclip

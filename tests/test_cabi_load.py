@@ -101,6 +101,8 @@ def test_sass_has_blackwell_instructions():
         pytest.skip("cuobjdump not on PATH")
     sass = subprocess.run(["cuobjdump", "-sass", os.path.join(ROOT, "mamba_clip_b200", "libmclip_b200.so")],
                           capture_output=True, text=True).stdout
-    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "STTM"):
+    # tcgen05.mma (CTA pairs), TMA loads / stores / reduce-adds, tcgen05.ld; G is handed over through shared memory,
+    # so there is no tcgen05.st (STTM) any more
+    for mnemonic in ("UTCHMMA.2CTA", "UTMALDG", "UTMASTG", "UTMAREDG", "LDTM"):
         assert mnemonic in sass, f"{mnemonic} missing from SASS"
     assert "HMMA.16816" not in sass  # no legacy mma.sync path
