@@ -12,8 +12,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmclip_b200.so")
-SOURCES = ["abi.cu", "simt_kernels.cu", "small_kernels.cu", "tc_kernels.cu", "tc_pair_lse.cu", "tc_gemm_tn.cu", "producer_kernels.cu"]
-HEADERS = ["common.cuh", "sm100_ptx.cuh", "tc_host.cuh", os.path.join("..", "..", "include", "mclip_b200.h")]
+SOURCES = ["abi.cu", "simt_kernels.cu", "small_kernels.cu", "tc_kernels.cu", "tc_bwd_persist.cu", "tc_pair_lse.cu", "tc_gemm_tn.cu", "producer_kernels.cu"]
+HEADERS = ["common.cuh", "sm100_ptx.cuh", "tc_host.cuh", "tc_bwd_common.cuh", os.path.join("..", "..", "include", "mclip_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
