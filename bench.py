@@ -185,16 +185,19 @@ def run_reference_arm(args):
         Bt = 32768
     else:
         Bt = B
-    iters = max(1, min(args.steps, 3))      # ~4 s per fwd+bwd at B=32768 on the box's 16 cores; BASELINE.md section 4: 1 + 3
-    value, t, kind, cores, what = reference_cpu_measure(Bt, D, iters=iters, warmup=1)
+    if Bt >= 8192:
+        iters, warm = max(1, min(args.steps, 3)), 1     # ~4 s per fwd+bwd at B=32768 on the box's 16 cores; BASELINE.md section 4: 1 + 3
+    else:
+        iters, warm = max(1, args.steps), max(1, args.warmup)   # milliseconds per step: the flags as given
+    value, t, kind, cores, what = reference_cpu_measure(Bt, D, iters=iters, warmup=warm)
     if Bt != B:
         value = value * Bt / B
         t = t * (B / Bt) ** 2
     base = {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
-            "sample": f"{what}, fp32, W=1, B={Bt} x D={D}: 1 warm-up + {iters} timed fwd+bwd" + (f"; {note}" if note else "")}
+            "sample": f"{what}, fp32, W=1, B={Bt} x D={D}: {warm} warm-up + {iters} timed fwd+bwd" + (f"; {note}" if note else "")}
     line = {
         "impl": "reference", "metric": cfg["metric"], "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": iters, "warmup": 1, "ms_per_step": t * 1e3,
+        "steps": iters, "warmup": warm, "ms_per_step": t * 1e3,
         "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": dict(workload_config(cfg, world),
                        note="CPU arm: the reference's ClipLoss at W=1 over the same global batch (fp32 upcast of the bf16 values, all host threads)"
