@@ -275,8 +275,8 @@ def parity_check(step, cfg, img_all, txt_all, a, b, ls, rank, world, dev, n_rows
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="C3", choices=sorted(CONFIGS))
     ap.add_argument("--batch", type=int, default=0, help="override the global batch of the chosen config")
