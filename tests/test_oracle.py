@@ -155,3 +155,23 @@ def test_reference_copy_matches_port_when_present():
     port = O.ref_port_single(img, txt, 14.2857, grad_output=3.0)
     assert torch.equal(loss.detach(), port.loss)
     assert torch.equal(a.grad, port.d_image) and torch.equal(b.grad, port.d_text) and torch.equal(s.grad, port.d_logit_scale)
+
+
+def test_euler_identity_holds_in_the_reference_outputs():
+    """The logits are homogeneous of degree 1 in each feature matrix and in logit_scale, so
+    sum_i <I_i, dI_i> = sum_j <T_j, dT_j> = logit_scale * d(logit_scale).  mclip_fused_grad takes d(logit_scale) from
+    this identity; here it is checked on the REFERENCE's own stored gradients."""
+    checked = 0
+    for k, case in enumerate(SINGLE_CASES):
+        if f"c{k}_di_full" not in SINGLE:
+            continue
+        img, txt = inputs_for(case)
+        di = torch.from_numpy(SINGLE[f"c{k}_di_full"]).double()
+        dt = torch.from_numpy(SINGLE[f"c{k}_dt_full"]).double()
+        want = case["ls"] * float(SINGLE[f"c{k}_dls"])
+        si, st = float((img.double() * di).sum()), float((txt.double() * dt).sum())
+        # fp32 reference gradients: the sums cancel to ~1e-6 of the sum of magnitudes
+        scale = float((img.double() * di).abs().sum()) + abs(want)
+        assert abs(si - want) <= 2e-5 * scale and abs(st - want) <= 2e-5 * scale, (k, si, st, want)
+        checked += 1
+    assert checked >= 10
