@@ -227,7 +227,8 @@ int mclip_small_pack(const void* a, const void* b, int64_t n, int in_dtype, int 
 /*
  * Development / measurement switches.  Read from the environment once at load time (MCLIP_BWD_PERSIST, MCLIP_FUSED_BWD,
  * MCLIP_DBG), never on the launch path; these calls change them afterwards.  Names: "bwd_persist" (persistent variant
- * of the CTA-pair backward kernel), "fused_bwd" (0 makes mclip_fused_grad_supported answer 0), "dbg" (profiling builds).
+ * of the CTA-pair backward kernel: 1 = always, 0 = never, -1 = chosen per launch shape, the default), "fused_bwd" (0 makes
+ * mclip_fused_grad_supported answer 0), "dbg" (profiling builds).
  */
 int mclip_set_option(const char* name, int value);
 int mclip_get_option(const char* name, int* value);

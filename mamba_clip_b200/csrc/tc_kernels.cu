@@ -1045,12 +1045,12 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 // Development switches are read from the environment ONCE, when the library is loaded (never on the launch path), and
 // can be changed afterwards through mclip_set_option (tests do that instead of re-reading the environment).
 struct Options {
-  int bwd_persist;   // MCLIP_BWD_PERSIST: persistent CTA-pair backward kernel (stream-K vehicle)
+  int bwd_persist;   // MCLIP_BWD_PERSIST: persistent CTA-pair backward kernel: -1 = by shape (default), 0 = never, 1 = always
   int dbg;           // MCLIP_DBG: development masks; only honoured by -DMCLIP_PROFILE builds
   int fused_bwd;     // MCLIP_FUSED_BWD: shared-recompute backward (one S recompute for dX and dY) where it applies
   Options() {
     auto geti = [](const char* k, int dflt) { const char* e = getenv(k); return e ? atoi(e) : dflt; };
-    bwd_persist = geti("MCLIP_BWD_PERSIST", 0);
+    bwd_persist = geti("MCLIP_BWD_PERSIST", -1);
     dbg = kProfile ? geti("MCLIP_DBG", 0) : 0;
     fused_bwd = geti("MCLIP_FUSED_BWD", 1);
   }
@@ -1192,7 +1192,7 @@ FwdPlan plan_fwd2(int64_t M, int64_t N, int64_t D) {
   return f;
 }
 
-struct Bwd2Plan { int kch; int kpairs; int ndh; int steps_total; int nsplit; int steps_per_split; uint32_t smem; };
+struct Bwd2Plan { int kch; int kpairs; int ndh; int steps_total; int nsplit; int steps_per_split; uint32_t smem; double cost; };
 
 // (Variants measured and removed in round 2, all numerically identical -- numbers in profiles/r1_ncu_summary.md section 3:
 // 4-CTA clusters with multicast Y tiles 1.95 vs 1.85 ms; G handed over through TMEM 1.61 vs 1.53 ms; transposed pair
@@ -1217,18 +1217,36 @@ Bwd2Plan plan_bwd2(int64_t M, int64_t N, int64_t D) {
     if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
   }
   b.nsplit = best;
+  b.cost = best_cost;
   b.steps_per_split = (int)ceil_div(b.steps_total, best);
   b.smem = D <= 512 ? kAlignSlack + 8 * kTile8K + 4 * kTile8K + kRing2 * kStage2 + 1536     // 64 KB X + 32 KB G + 4 x 32 KB ring
                     : kAlignSlack + 12 * kTile8K + 4 * kTile8K + 3 * kStage2 + 1536;        // 96 KB X + 32 KB G + 3 x 32 KB ring
   return b;
 }
 
-// persistent pair kernel: P pairs walk U = row_blocks x steps units
-// Option bwd_persist (MCLIP_BWD_PERSIST=1 at load, or mclip_set_option) selects the persistent pair kernel.  Measured (B200, bf16, D = 512): 1.50 vs 1.47 ms at
-// 32768 x 32768 and 194 vs 198 us at 4096 x 32768 (the W = 8 shape) -- per step both kernels spend the same ~18 % of
-// the issue thread's time waiting for TMA data, and at W = 1 the launch runs into the board power cap either way, so
-// removing the wave quantisation and the CTA prologues buys nothing yet.  Kept opt-in; passes the same parity tests.
-bool use_persistent_bwd() { return options().bwd_persist != 0; }
+// Persistent pair kernel (tc_bwd_persist.cu): P pairs walk U = row_blocks x steps units, so the launch has no wave
+// quantisation, at the price of a per-pair item switch (X reload, accumulator drain) and f32 partials + a fix-up pass for
+// the row blocks a range boundary cuts.  Option bwd_persist: 1 = always, 0 = never, -1 (default) = by shape, taken when
+//   (a) the best split grid leaves more than 8 % of its pair-slot time idle,
+//   (b) a pair's range is long (>= 96 steps) and
+//   (c) a row block is not shared by many pairs (steps per row block <= 1.5 x steps per pair).
+// Measured whole calls, split grid vs persistent (B200, bf16, D = 512, us; profiles/r2_summary.md section 11):
+//   M x N          32768x32768  16384x32768  20480x32768  10240x32768  8192x32768  16384x16384 | 4096x32768  4096x65536
+//   split grid        1470          780         1003          578         460          452     |    232         442
+//   persistent        1500          774          968          522         384          403     |    260         526
+//   rule picks        split        split      persistent   persistent  persistent  persistent  |   split       split
+// (8192 x 32768 is a rank of C3 on 4 GPUs: 64 row blocks for 74 pair slots.  The two shapes on the right fail (c): with 32
+// row blocks every one is cut two or three times and the persistent kernel loses.)
+double plan_bwd2_cost(int64_t M, int64_t N, int64_t D) { return plan_bwd2(M, N, D).cost; }
+bool use_persistent_bwd(int64_t M, int64_t N, int64_t D) {
+  const int mode = options().bwd_persist;
+  if (mode >= 0) return mode != 0;
+  if (D > 512) return false;
+  const double units = (double)ceil_div(M, 128) * (double)ceil_div(N, 256);
+  const double per_pair = units / pair_slots();
+  const double steps = (double)ceil_div(N, 256);
+  return per_pair >= 96.0 && steps <= 1.5 * per_pair && plan_bwd2_cost(M, N, D) > 1.08 * (per_pair + 4.0);
+}
 
 // workspace carve-up shared by the size query and the launcher
 struct BwdWs { size_t acc, rd, ly2, y16, total; };
@@ -1823,7 +1841,7 @@ int tc_block_grad(const BlockGradArgs& a) {
   if (((uintptr_t)a.X | (uintptr_t)a.Y | (uintptr_t)a.dX) & 15) { set_error("block_grad(tcgen05): X/Y/dX must be 16-byte aligned"); return MCLIP_ERR_INVALID; }
   if (!(a.w_row > 0.f) || a.w_col < 0.f) { set_error("block_grad(tcgen05): needs w_row > 0 and w_col >= 0"); return MCLIP_ERR_INVALID; }
   // D <= 512: both S buffers in TMEM; 512 < D <= 768: one S buffer, X tiles 8..11 resident too (kNX = 12)
-  return (a.D <= 512 && use_persistent_bwd()) ? tc_block_grad2p(a) : tc_block_grad2(a);
+  return (a.D <= 512 && use_persistent_bwd(a.M, a.N, a.D)) ? tc_block_grad2p(a) : tc_block_grad2(a);
 }
 
 }  // namespace mclip

@@ -73,9 +73,10 @@ def test_argument_validation_without_gpu(lib):
     assert lib.mclip_small_pack(None, None, 10, 1, 1, None, None) == 1
     assert lib.mclip_set_option(b"no_such_option", 1) == 1
     import ctypes as _ct
-    v = _ct.c_int(-1)
+    v, old = _ct.c_int(-7), _ct.c_int(-7)
+    assert lib.mclip_get_option(b"bwd_persist", _ct.byref(old)) == 0 and old.value in (-1, 0, 1)
     assert lib.mclip_set_option(b"bwd_persist", 1) == 0 and lib.mclip_get_option(b"bwd_persist", _ct.byref(v)) == 0 and v.value == 1
-    assert lib.mclip_set_option(b"bwd_persist", 0) == 0
+    assert lib.mclip_set_option(b"bwd_persist", old.value) == 0
     assert lib.mclip_pair_supported(4096, 4096, 512, 512, 512, 0) == 0        # fp32: FFMA path
     for op in (2, 3):                                                          # PAIR_LSE, PAIR_REF workspaces
         assert lib.mclip_workspace_bytes(32768, 32768, 512, 1, op, 0, ctypes.byref(n)) == 0 and n.value > 0

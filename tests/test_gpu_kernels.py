@@ -293,13 +293,48 @@ def test_block_grad_persistent_pair_kernel(M, N, D, ls, diag_off, w, persistent_
     assert float((rd.cpu().double() - ref_rd).abs().max()) <= 2e-3 * max(1.0, float(ref_rd.abs().max()))
 
 
+def test_block_grad_shape_selected_persistent_kernel_matches_split_grid():
+    """Default option (-1): the launch shape decides.  8192 x 32768 x 512 (a rank of C3 on 4 GPUs: 64 row blocks for 74 pair
+    slots) takes the persistent kernel; its dX / rowdot must agree with the split-grid kernel (option 0) on the same inputs
+    to summation-order noise, and both with the fp64 oracle on a sample of rows."""
+    be = backend(TC)
+    old = be.get_option("bwd_persist")
+    M, N, D, ls = 8192, 32768, 512, 14.2857
+    x, y = feats(M, N, D, torch.bfloat16, seed=77, correlated=False)
+    xc, yc = x.cuda(), y.cuda()
+    lsd, go = torch.tensor([ls], device="cuda"), torch.tensor([2.0], device="cuda")
+    lse_x = be.row_lse(xc, yc, lsd, 0, False)[0]
+    lse_y = be.row_lse(yc, xc, lsd, 0, False)[0]
+    outs = {}
+    try:
+        for mode in (-1, 0):
+            be.set_option("bwd_persist", mode)
+            n0 = be.launch_count()
+            dx, rd = be.block_grad(xc, yc, lsd, go, lse_x, lse_y, 0, 1.0, 1.0, 2.0, 1.0 / (2 * N), True)
+            torch.cuda.synchronize()
+            outs[mode] = (dx.float(), rd.clone(), be.launch_count() - n0)
+    finally:
+        be.set_option("bwd_persist", old)
+    (dx_a, rd_a, _), (dx_s, rd_s, _) = outs[-1], outs[0]
+    assert float((dx_a - dx_s).norm()) <= 3e-3 * float(dx_s.norm())          # two bf16 roundings of the same f32 sums
+    assert float((rd_a - rd_s).abs().max()) <= 1e-4 * max(1.0, float(rd_s.abs().max()))
+    rows = torch.arange(0, M, 61)
+    xf, yf = x.float(), y.float()
+    alpha = 2.0 * ls / (2 * N)
+    ref_dx, _ = O.block_grad(xf[rows], yf, ls, lse_x.cpu()[rows].double(), lse_y.cpu().double(), 0, 1.0, 1.0, 0.0, alpha=alpha)
+    ref_dx = ref_dx - alpha * 2.0 * yf[rows].double()          # the positive pair of row r sits in column r
+    assert float((dx_a.cpu()[rows].double() - ref_dx).norm()) <= 2e-3 * float(ref_dx.norm())
+    assert float((dx_s.cpu()[rows].double() - ref_dx).norm()) <= 2e-3 * float(ref_dx.norm())
+
+
 @pytest.fixture()
 def persistent_backward():
     """Switch the library option for the duration of a test (the environment is only read when the library loads)."""
     be = backend(TC)
+    old = be.get_option("bwd_persist")
     be.set_option("bwd_persist", 1)
     yield
-    be.set_option("bwd_persist", 0)
+    be.set_option("bwd_persist", old)
 
 
 def load_single():
