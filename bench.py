@@ -18,6 +18,7 @@ oracle port) on the host cores at the configuration's true size.
 from __future__ import annotations
 
 import argparse
+import atexit
 import json
 import os
 import statistics
@@ -60,57 +61,87 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 20 ms from the last warm-up steps to the end of the timed regions."""
+    """nvidia-smi clocks / throttle reasons, one sample every 20 ms, each stamped with its arrival time; `stop(t0, t1)` keeps
+    the samples that arrived inside [t0, t1] (time.perf_counter(): the device-timed region through the end of the e2e
+    region).  If none did (a region shorter than one period), the samples closest to the window are used and the line says so."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index: int):
+    def __init__(self, index: int, max_seconds: int = 960):
         self.index = index
-        self.rows = []
+        self.max_seconds = int(max_seconds)
+        self.rows = []          # (arrival time, csv line)
         self.proc = None
         self.thread = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
+            # bounded lifetime even if this process dies without cleaning up (the watchdog uses os._exit)
+            self.proc = subprocess.Popen(["timeout", "-s", "TERM", str(self.max_seconds), "nvidia-smi", "-i", str(self.index),
+                                          f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            atexit.register(self._kill)
         except Exception:
             self.proc = None
             return
 
         def pump():
-            for line in self.proc.stdout:
-                self.rows.append(line.strip())
+            try:
+                for line in self.proc.stdout:
+                    self.rows.append((time.perf_counter(), line.strip()))
+            except Exception:
+                pass
         self.thread = threading.Thread(target=pump, daemon=True)
         self.thread.start()
 
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+    def _kill(self):
         try:
-            self.proc.wait(timeout=5)
+            if self.proc is not None and self.proc.poll() is None:
+                self.proc.terminate()
         except Exception:
-            self.proc.kill()
-        sm, mx, reasons, pw = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+            pass
+
+    @classmethod
+    def summarise(cls, rows, t0=None, t1=None):
+        parsed = []
+        for t, r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
             try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
-                pw.append(float(f[2]))
+                parsed.append((t, float(f[0]), float(f[1]), float(f[2]), [v.lower().startswith("active") for v in f[3:7]]))
             except ValueError:
                 continue
-            for n, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        busy = [s for s, p in zip(sm, pw) if p > 300] or sm
+        window = "all samples"
+        if t0 is not None and t1 is not None and parsed:
+            inside = [p for p in parsed if t0 <= p[0] <= t1 + 0.03]       # a sample lands up to one period after it was taken
+            if inside:
+                parsed, window = inside, "samples that arrived inside the timed regions (device-timed steps through the e2e steps)"
+            else:
+                mid = 0.5 * (t0 + t1)
+                parsed = sorted(parsed, key=lambda p: abs(p[0] - mid))[:2]
+                window = "timed regions shorter than one 20 ms sampling period: the two samples nearest to them"
+        sm = [p[1] for p in parsed]
+        mx = [p[2] for p in parsed]
+        pw = [p[3] for p in parsed]
+        reasons = sorted({n for p in parsed for n, on in zip(cls.NAMES, p[4]) if on})
+        busy = [s_ for s_, p_ in zip(sm, pw) if p_ > 300] or sm
         return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(pw) if pw else None}
+                "reasons": reasons, "samples": len(sm), "power_w_max": max(pw) if pw else None, "window": window}
+
+    def stop(self, t0=None, t1=None):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        try:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+            return self.summarise(list(self.rows), t0, t1)
+        except Exception as e:          # never let the clock report take the bench line down
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling failed: %r" % (e,)], "samples": 0}
 
 
 def resolve_config(args, world):
@@ -343,6 +374,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    # nvidia-smi needs 0.1-0.3 s before its first sample and the timed region of a multi-GPU run lasts tens of milliseconds:
+    # start it now (it streams a sample every 20 ms from here on) and keep only the samples that arrive inside the timed
+    # regions (ClockSampler.stop).
+    sampler = ClockSampler(local_rank, max_seconds=int(args.max_seconds) + 30)
+    if rank == 0:
+        sampler.start()
+
     # ---- parity of the exact path that is timed below (first call: eager; graphs replay the same kernels) ----
     c0 = be.launch_count()
     step(img_d, txt_d)                     # always eager (graphs are captured on the third call of a shape)
@@ -357,25 +395,7 @@ def main():
             raise SystemExit(4)
 
     # ---- device-resident timing ----
-    # nvidia-smi delivers its first sample 0.1-0.3 s after it starts and the timed region of a multi-GPU run lasts only tens
-    # of milliseconds: start the sampler before the warm-up and keep the GPU under the very same load (untimed steps) for
-    # ~0.4 s first, so that the samples -- taken from there to the end of the end-to-end region -- are clocks under this load.
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     for _ in range(max(args.warmup - 1, 3 if not args.no_graphs else 0)):
-        step(img_d, txt_d)
-    w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    w0.record()
-    for _ in range(3):
-        step(img_d, txt_d)
-    w1.record()
-    torch.cuda.synchronize(dev)
-    est_ms = torch.tensor([max(w0.elapsed_time(w1) / 3.0, 0.02)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(est_ms, op=dist.ReduceOp.MAX)      # every rank must run the same number of steps (collectives inside)
-    n_settle = min(2000, int(400.0 / float(est_ms)) + 1)
-    for _ in range(n_settle):
         step(img_d, txt_d)
     barrier()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -446,9 +466,8 @@ def main():
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = B / (float(e2e_ms) * 1e-3)
-    clocks = sampler.stop() if rank == 0 else None
-    if clocks is not None:
-        clocks["window"] = "nvidia-smi every 20 ms over %d untimed settle steps of the same load, the timed region and the e2e region" % n_settle
+    barrier()
+    clocks = sampler.stop(t_wall0, time.perf_counter()) if rank == 0 else None
 
     # ---- dominant kernel(s) of the step timed alone on this rank's shapes ----
     # W = 1, D <= 512: the shared-recompute backward (mclip_fused_grad: tc_block_grad2_kernel<store G> panels on the main

@@ -67,3 +67,40 @@ def test_gpu_arm_fails_loudly_without_a_gpu():
                        cwd=ROOT, capture_output=True, text=True, timeout=300)
     assert r.returncode != 0
     assert _json_lines(r.stdout) == []          # no number from a CPU path
+
+
+def _load_bench():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(ROOT, "bench.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def test_clock_sampler_keeps_the_samples_of_the_timed_window():
+    m = _load_bench()
+    idle = "1965, 1965, 120.5, Not Active, Not Active, Not Active, Not Active"
+    rows = [(0.10, idle), (1.00, "1700, 1965, 640.0, Not Active, Not Active, Not Active, Active"),
+            (1.02, "1650, 1965, 650.0, Not Active, Not Active, Not Active, Active"), (1.30, idle), (1.40, "garbage")]
+    r = m.ClockSampler.summarise(rows, 0.99, 1.03)
+    assert r["samples"] == 2 and r["sm_mhz"] == 1675.0 and r["reasons"] == ["sw_power_cap"] and r["power_w_max"] == 650.0
+    r = m.ClockSampler.summarise(rows, 0.50, 0.51)                 # window shorter than a period: nearest samples, and says so
+    assert r["samples"] == 2 and "nearest" in r["window"]
+    assert m.ClockSampler.summarise([], 0.0, 1.0)["samples"] == 0
+
+
+def test_clock_sampler_process_is_started_filtered_and_terminated(tmp_path, monkeypatch):
+    import time
+    fake = tmp_path / "nvidia-smi"
+    fake.write_text('#!/bin/bash\nwhile true; do echo "1800, 1965, 500.0, Not Active, Not Active, Not Active, Active"; sleep 0.02; done\n')
+    fake.chmod(0o755)
+    monkeypatch.setenv("PATH", str(tmp_path) + os.pathsep + os.environ["PATH"])
+    m = _load_bench()
+    c = m.ClockSampler(0, max_seconds=10)
+    c.start()
+    time.sleep(0.3)
+    t0 = time.perf_counter()
+    time.sleep(0.1)
+    r = c.stop(t0, time.perf_counter())
+    assert 2 <= r["samples"] <= 10 and r["sm_mhz"] == 1800.0 and r["reasons"] == ["sw_power_cap"]
+    assert c.proc.poll() is not None            # no sampler left behind
